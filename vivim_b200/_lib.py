@@ -1,0 +1,86 @@
+"""ctypes binding of libvivim_b200.so (include/vivim_b200.h).  No fallback: if the library is
+missing or a kernel call fails, a RuntimeError is raised."""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import POINTER, Structure, c_char_p, c_int, c_int32, c_int64, c_void_p
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "lib", "libvivim_b200.so")
+
+VV_F32, VV_F16, VV_BF16 = 0, 1, 2
+VV_SCAN_UNIT = 256
+
+
+class ConvArgs(Structure):
+    """vv_conv1d_args"""
+    _fields_ = [
+        ("x", c_void_p), ("weight", c_void_p), ("bias", c_void_p), ("out", c_void_p),
+        ("dout", c_void_p), ("dx", c_void_p), ("dweight", c_void_p), ("dbias", c_void_p),
+        ("batch", c_int32), ("dim", c_int32), ("seqlen", c_int32), ("width", c_int32),
+        ("x_bs", c_int64), ("x_ds", c_int64), ("out_bs", c_int64), ("out_ds", c_int64),
+        ("dout_bs", c_int64), ("dout_ds", c_int64), ("dx_bs", c_int64), ("dx_ds", c_int64),
+        ("io_dtype", c_int32), ("w_dtype", c_int32), ("silu", c_int32),
+    ]
+
+
+class ScanArgs(Structure):
+    """vv_scan_args"""
+    _fields_ = [
+        ("u", c_void_p), ("delta", c_void_p), ("A", c_void_p), ("Bm", c_void_p), ("Cm", c_void_p),
+        ("D", c_void_p), ("z", c_void_p), ("delta_bias", c_void_p),
+        ("out", c_void_p), ("out_z", c_void_p), ("last_state", c_void_p),
+        ("agg", c_void_p), ("chk", c_void_p), ("radj", c_void_p),
+        ("dout", c_void_p), ("du", c_void_p), ("ddelta", c_void_p), ("dz", c_void_p),
+        ("dA", c_void_p), ("dB", c_void_p), ("dC", c_void_p), ("dD", c_void_p),
+        ("ddelta_bias", c_void_p),
+        ("batch", c_int32), ("dim", c_int32), ("seqlen", c_int32), ("dstate", c_int32),
+        ("ngroups", c_int32),
+        ("u_bs", c_int64), ("u_ds", c_int64), ("delta_bs", c_int64), ("delta_ds", c_int64),
+        ("z_bs", c_int64), ("z_ds", c_int64), ("out_bs", c_int64), ("out_ds", c_int64),
+        ("outz_bs", c_int64), ("outz_ds", c_int64),
+        ("A_ds", c_int64), ("A_ns", c_int64),
+        ("B_bs", c_int64), ("B_gs", c_int64), ("B_ns", c_int64),
+        ("C_bs", c_int64), ("C_gs", c_int64), ("C_ns", c_int64),
+        ("dout_bs", c_int64), ("dout_ds", c_int64), ("du_bs", c_int64), ("du_ds", c_int64),
+        ("ddelta_bs", c_int64), ("ddelta_ds", c_int64), ("dz_bs", c_int64), ("dz_ds", c_int64),
+        ("io_dtype", c_int32), ("delta_softplus", c_int32),
+    ]
+
+
+# every symbol include/vivim_b200.h declares (checked by tests/test_cabi.py)
+EXPORTS = ("vv_version", "vv_last_error", "vv_scan_num_units", "vv_conv1d_fwd", "vv_conv1d_bwd",
+           "vv_scan_fwd", "vv_scan_bwd", "vv_last_launch_count", "vv_scan_set_pass_mask")
+
+_lib = None
+
+
+def lib() -> ctypes.CDLL:
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} is missing: build it with `python -m vivim_b200.build` "
+                "(there is no CPU or PyTorch fallback for the Vivim Mamba hot path)")
+        L = ctypes.CDLL(LIB_PATH)
+        L.vv_version.restype = c_int
+        L.vv_last_error.restype = c_char_p
+        L.vv_last_launch_count.restype = c_int
+        L.vv_scan_set_pass_mask.argtypes = [c_int]
+        L.vv_scan_set_pass_mask.restype = c_int
+        L.vv_scan_num_units.argtypes = [c_int]
+        L.vv_scan_num_units.restype = c_int
+        for name, argt in (("vv_conv1d_fwd", ConvArgs), ("vv_conv1d_bwd", ConvArgs),
+                           ("vv_scan_fwd", ScanArgs), ("vv_scan_bwd", ScanArgs)):
+            fn = getattr(L, name)
+            fn.argtypes = [POINTER(argt), c_void_p]
+            fn.restype = c_int
+        _lib = L
+    return _lib
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        msg = lib().vv_last_error().decode("utf-8", "replace")
+        raise RuntimeError(f"{what} failed (code {rc}): {msg}")

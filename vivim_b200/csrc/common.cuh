@@ -1,0 +1,130 @@
+// common.cuh -- element-type helpers shared by the conv1d and selective-scan kernels (sm_100a).
+#pragma once
+
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace vv {
+
+constexpr int kWarp = 32;
+constexpr int kVecElems = 8;          // sequence positions one thread owns per unit
+constexpr float kLog2e = 1.4426950408889634f;
+
+// ---------------------------------------------------------------- scalar conversions
+template <typename T> __device__ __forceinline__ float to_f32(T v);
+template <> __device__ __forceinline__ float to_f32<float>(float v) { return v; }
+template <> __device__ __forceinline__ float to_f32<__half>(__half v) { return __half2float(v); }
+template <> __device__ __forceinline__ float to_f32<__nv_bfloat16>(__nv_bfloat16 v) { return __bfloat162float(v); }
+
+template <typename T> __device__ __forceinline__ T from_f32(float v);
+template <> __device__ __forceinline__ float from_f32<float>(float v) { return v; }
+template <> __device__ __forceinline__ __half from_f32<__half>(float v) { return __float2half_rn(v); }
+template <> __device__ __forceinline__ __nv_bfloat16 from_f32<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
+
+// ---------------------------------------------------------------- 8-element row segments
+// Vector path: `p` is 16-byte aligned and all 8 elements are in range (128-bit coalesced accesses).
+template <typename T> __device__ __forceinline__ void load8_vec(const T* __restrict__ p, float (&v)[8]);
+
+template <> __device__ __forceinline__ void load8_vec<float>(const float* __restrict__ p, float (&v)[8]) {
+    const float4 a = __ldg(reinterpret_cast<const float4*>(p));
+    const float4 b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
+    v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+template <> __device__ __forceinline__ void load8_vec<__nv_bfloat16>(const __nv_bfloat16* __restrict__ p, float (&v)[8]) {
+    const uint4 r = __ldg(reinterpret_cast<const uint4*>(p));
+    const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {          // bf16 -> f32 is a 16-bit shift
+        v[2 * i] = __uint_as_float(w[i] << 16);
+        v[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+    }
+}
+template <> __device__ __forceinline__ void load8_vec<__half>(const __half* __restrict__ p, float (&v)[8]) {
+    const uint4 r = __ldg(reinterpret_cast<const uint4*>(p));
+    const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w[i]));
+        v[2 * i] = f.x;
+        v[2 * i + 1] = f.y;
+    }
+}
+
+template <typename T> __device__ __forceinline__ void store8_vec(T* __restrict__ p, const float (&v)[8]);
+
+template <> __device__ __forceinline__ void store8_vec<float>(float* __restrict__ p, const float (&v)[8]) {
+    reinterpret_cast<float4*>(p)[0] = make_float4(v[0], v[1], v[2], v[3]);
+    reinterpret_cast<float4*>(p)[1] = make_float4(v[4], v[5], v[6], v[7]);
+}
+template <> __device__ __forceinline__ void store8_vec<__nv_bfloat16>(__nv_bfloat16* __restrict__ p, const float (&v)[8]) {
+    uint4 r;
+    uint32_t* w = reinterpret_cast<uint32_t*>(&r);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+        w[i] = *reinterpret_cast<const uint32_t*>(&h);
+    }
+    *reinterpret_cast<uint4*>(p) = r;
+}
+template <> __device__ __forceinline__ void store8_vec<__half>(__half* __restrict__ p, const float (&v)[8]) {
+    uint4 r;
+    uint32_t* w = reinterpret_cast<uint32_t*>(&r);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const __half2 h = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
+        w[i] = *reinterpret_cast<const uint32_t*>(&h);
+    }
+    *reinterpret_cast<uint4*>(p) = r;
+}
+
+// Row segment [t0, t0+8) of a row of length L starting at `row`.  kVec: the row base is 16-byte
+// aligned and L % 8 == 0, so a segment is either fully inside or fully outside.  Positions outside
+// [0, L) read as `fill` and are not written.
+template <typename T, bool kVec>
+__device__ __forceinline__ void load8(const T* __restrict__ row, int t0, int L, float (&v)[8], float fill = 0.f) {
+    if (kVec) {
+        if (t0 >= 0 && t0 < L) {
+            load8_vec<T>(row + t0, v);
+        } else {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[i] = fill;
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int t = t0 + i;
+            v[i] = (t >= 0 && t < L) ? to_f32<T>(row[t]) : fill;
+        }
+    }
+}
+
+template <typename T, bool kVec>
+__device__ __forceinline__ void store8(T* __restrict__ row, int t0, int L, const float (&v)[8]) {
+    if (kVec) {
+        if (t0 < L) store8_vec<T>(row + t0, v);
+    } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int t = t0 + i;
+            if (t < L) row[t] = from_f32<T>(v[i]);
+        }
+    }
+}
+
+// ---------------------------------------------------------------- math (fast-math forms, like the
+// reference build's --use_fast_math: mamba/setup.py:145, causal-conv1d/setup.py:143)
+__device__ __forceinline__ float sigmoid_f(float v) { return __fdividef(1.f, 1.f + __expf(-v)); }
+
+// F.softplus with threshold 20 (selective_scan_fwd_kernel.cuh:153-156)
+__device__ __forceinline__ float softplus_f(float v) { return v <= 20.f ? log1pf(__expf(v)) : v; }
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+}  // namespace vv

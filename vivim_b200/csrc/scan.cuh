@@ -1,0 +1,515 @@
+// scan.cuh -- fused selective scan forward / backward for sm_100a.
+//
+// Replaces selective_scan_fwd_kernel / selective_scan_bwd_kernel of the reference
+// (mamba/csrc/selective_scan/selective_scan_fwd_kernel.cuh:67-303, selective_scan_bwd_kernel.cuh:75-489).
+// The algebra is the reference's: the associative operator (a0,b0)o(a1,b1) = (a1 a0, a1 b0 + b1)
+// (selective_scan_common.h:110-115), softplus with threshold 20, exp2f(dt * A * log2e).
+//
+// Design (B200-first, not a port).  The reference walks a whole (batch, channel) row inside one
+// CTA, chunk after chunk; at Vivim's shapes that is 128..1024 CTAs each serialising up to 20480
+// steps x 16 states.  Here the sequence is cut into UNITS of 256 positions and every
+// (batch, channel, unit) is an independent piece of work for one warp:
+//
+//   pass 1  scan_agg_kernel      per unit and state: the unit's aggregate (decay product, local state)
+//   pass 2  scan_carry_kernel    per (row, state): a serial fold over the units' aggregates
+//                                -> state entering each unit (forward: the checkpoint tensor `chk`,
+//                                   saved for the backward; reverse: the adjoint carry `radj`)
+//   pass 3  scan_fwd_main_kernel / scan_bwd_main_kernel   per unit, seeded by its carry
+//
+// so B*D*ceil(L/256) warps are in flight (10240 at the B=1 stage-1 shape) and no CTA waits on
+// another.  The backward recomputes the forward states of a unit from `chk` (checkpointed chunk
+// states, recomputed in the backward) and never reads a saved `out`.
+//
+// Inside a warp: lane l owns positions [8l, 8l+8) of the unit (one 128-bit access per streamed
+// tensor, 512 contiguous bytes per warp request).  For one state n the lane runs the recurrence over
+// its 8 positions in registers (exp2 evaluated once per element and kept), the 32 lane aggregates
+// are combined by a 5-step warp-shuffle scan, and a second in-register sweep produces the states.
+// B and C rows of the unit are staged once per CTA in shared memory as fp32 (so the bf16->fp32
+// conversion is paid once per CTA, not once per channel) in a slot order that makes each lane's two
+// 128-bit reads bank-conflict free, and are reused by every channel the CTA walks.
+// dB/dC are reduced over the channels of a CTA in shared memory (each warp owns a different state
+// row between two barriers, so the read-modify-write needs no atomics) and leave the CTA as one
+// 128-bit red.global.add per 4 positions -- D/(rows per CTA)-way contention instead of the
+// reference's D-way scalar atomics (selective_scan_bwd_kernel.cuh:298-316).
+#pragma once
+
+#include "../../include/vivim_b200.h"
+#include "common.cuh"
+
+namespace vv {
+
+constexpr int kUnit = VV_SCAN_UNIT;       // positions per unit = 32 lanes x 8
+constexpr int kSlots = 64;                // float4 slots per state row of a staged tile
+constexpr int kMaxState = 32;             // states are held one per lane
+constexpr int kDaPitch = 33;              // padded pitch of the per-lane dA scratch
+
+static_assert(kUnit == kWarp * kVecElems, "a unit is one warp x 8 positions");
+
+// ---------------------------------------------------------------- warp scans of (P, X) pairs
+// forward: lane l ends with the aggregate of lanes 0..l
+__device__ __forceinline__ void warp_scan_fwd(float& P, float& X, int lane) {
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const float Pu = __shfl_up_sync(0xffffffffu, P, o);
+        const float Xu = __shfl_up_sync(0xffffffffu, X, o);
+        if (lane >= o) {
+            X = fmaf(P, Xu, X);
+            P *= Pu;
+        }
+    }
+}
+// reverse: lane l ends with the aggregate of lanes l..31 (recurrence runs right to left)
+__device__ __forceinline__ void warp_scan_rev(float& P, float& X, int lane) {
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const float Pd = __shfl_down_sync(0xffffffffu, P, o);
+        const float Xd = __shfl_down_sync(0xffffffffu, X, o);
+        if (lane + o < 32) {
+            X = fmaf(P, Xd, X);
+            P *= Pd;
+        }
+    }
+}
+
+// ---------------------------------------------------------------- staging of B / C unit tiles
+// tile[n * 64 + l]      = positions 8l .. 8l+3 of state row n
+// tile[n * 64 + 32 + l] = positions 8l+4 .. 8l+7
+template <typename T, bool kVec>
+__device__ __forceinline__ void fill_tile(float4* __restrict__ tile, const T* __restrict__ base, int64_t row_stride,
+                                          int N, int unit, int L) {
+    for (int idx = threadIdx.x; idx < N * 32; idx += blockDim.x) {
+        const int n = idx >> 5, l = idx & 31;
+        float v[8];
+        load8<T, kVec>(base + n * row_stride, unit * kUnit + l * kVecElems, L, v);
+        tile[n * kSlots + l] = make_float4(v[0], v[1], v[2], v[3]);
+        tile[n * kSlots + 32 + l] = make_float4(v[4], v[5], v[6], v[7]);
+    }
+}
+
+__device__ __forceinline__ void read_tile(const float4* __restrict__ tile, int n, int lane, float (&v)[8]) {
+    const float4 lo = tile[n * kSlots + lane];
+    const float4 hi = tile[n * kSlots + 32 + lane];
+    v[0] = lo.x; v[1] = lo.y; v[2] = lo.z; v[3] = lo.w;
+    v[4] = hi.x; v[5] = hi.y; v[6] = hi.z; v[7] = hi.w;
+}
+
+// dt = softplus?(delta + bias) for this lane's 8 positions; exactly 0 outside [0, L) so that padded
+// positions are the scan identity (decay 1, drive 0).
+template <typename T, bool kVec>
+__device__ __forceinline__ void load_dt(const T* __restrict__ row, int t0, int L, float bias, bool softplus,
+                                        float (&dt)[8]) {
+    load8<T, kVec>(row, t0, L, dt);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        float v = dt[i] + bias;
+        if (softplus) v = softplus_f(v);
+        dt[i] = (t0 + i < L) ? v : 0.f;
+    }
+}
+
+struct RowCoord {
+    int b, d, g, unit, lane, warp;
+    int64_t row;  // b * dim + d
+};
+
+__device__ __forceinline__ RowCoord row_coord(const vv_scan_args& a, int rows_seq, int k) {
+    RowCoord c;
+    c.lane = threadIdx.x & 31;
+    c.warp = threadIdx.x >> 5;
+    const int W = blockDim.x >> 5;
+    c.unit = blockIdx.x;
+    c.b = blockIdx.z;
+    c.d = (blockIdx.y * rows_seq + k) * W + c.warp;
+    c.g = c.d / (a.dim / a.ngroups);
+    c.row = (int64_t)c.b * a.dim + c.d;
+    return c;
+}
+
+// ================================================================ pass 1: unit aggregates
+// kRev = false: (P, X) of h_t = a_t h_{t-1} + dt_t B_t u_t over the unit        (uses u, B)
+// kRev = true : (P, X) of r_t = a_{t+1} r_{t+1} + g_t C_t, g = dout*silu(z)    (uses dout, z, C)
+template <typename T, bool kVec, bool kRev>
+__global__ void __launch_bounds__(128) scan_agg_kernel(const vv_scan_args a, const int rows_seq) {
+    extern __shared__ float4 smem4[];
+    float4* tile = smem4;
+    const int L = a.seqlen, N = a.dstate;
+    {
+        const RowCoord c0 = row_coord(a, rows_seq, 0);
+        const T* m = kRev ? reinterpret_cast<const T*>(a.Cm) + c0.b * a.C_bs + c0.g * a.C_gs
+                          : reinterpret_cast<const T*>(a.Bm) + c0.b * a.B_bs + c0.g * a.B_gs;
+        fill_tile<T, kVec>(tile, m, kRev ? a.C_ns : a.B_ns, N, c0.unit, L);
+    }
+    __syncthreads();
+    const int U = gridDim.x;
+    for (int k = 0; k < rows_seq; ++k) {
+        const RowCoord c = row_coord(a, rows_seq, k);
+        const int lane = c.lane;
+        const int t0 = c.unit * kUnit + lane * kVecElems;
+        const float bias = a.delta_bias ? a.delta_bias[c.d] : 0.f;
+        float dt[8], coef[8];
+        load_dt<T, kVec>(reinterpret_cast<const T*>(a.delta) + c.b * a.delta_bs + c.d * a.delta_ds, t0, L, bias,
+                         a.delta_softplus != 0, dt);
+        float sum_dt = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) sum_dt += dt[i];
+        if (!kRev) {
+            load8<T, kVec>(reinterpret_cast<const T*>(a.u) + c.b * a.u_bs + c.d * a.u_ds, t0, L, coef);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) coef[i] *= dt[i];
+        } else {
+            load8<T, kVec>(reinterpret_cast<const T*>(a.dout) + c.b * a.dout_bs + c.d * a.dout_ds, t0, L, coef);
+            if (a.z) {
+                float zv[8];
+                load8<T, kVec>(reinterpret_cast<const T*>(a.z) + c.b * a.z_bs + c.d * a.z_ds, t0, L, zv);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) coef[i] *= zv[i] * sigmoid_f(zv[i]);
+            }
+            // the reverse recurrence multiplies by the decay of the NEXT position
+            float dt_next = __shfl_down_sync(0xffffffffu, dt[0], 1);
+            if (lane == 31) {
+                const int tn = t0 + kVecElems;
+                dt_next = 0.f;
+                if (tn < L) {
+                    float v = to_f32<T>(reinterpret_cast<const T*>(a.delta)[c.b * a.delta_bs + c.d * a.delta_ds + tn]) + bias;
+                    dt_next = a.delta_softplus ? softplus_f(v) : v;
+                }
+            }
+            sum_dt = sum_dt - dt[0] + dt_next;
+        }
+        const float A2_l = lane < N ? a.A[c.d * a.A_ds + lane * a.A_ns] * kLog2e : 0.f;
+        float myP = 1.f, myX = 0.f;
+        for (int n = 0; n < N; ++n) {
+            const float A2 = __shfl_sync(0xffffffffu, A2_l, n);
+            float m[8];
+            read_tile(tile, n, lane, m);
+            float X;
+            if (!kRev) {
+                X = 0.f;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) X = fmaf(exp2f(dt[i] * A2), X, coef[i] * m[i]);
+            } else {
+                X = coef[7] * m[7];
+#pragma unroll
+                for (int i = 6; i >= 0; --i) X = fmaf(exp2f(dt[i + 1] * A2), X, coef[i] * m[i]);
+            }
+            float P = exp2f(A2 * sum_dt);
+            if (!kRev) warp_scan_fwd(P, X, lane); else warp_scan_rev(P, X, lane);
+            const float Pt = __shfl_sync(0xffffffffu, P, kRev ? 0 : 31);
+            const float Xt = __shfl_sync(0xffffffffu, X, kRev ? 0 : 31);
+            if (lane == n) { myP = Pt; myX = Xt; }
+        }
+        if (lane < N)
+            reinterpret_cast<float2*>(a.agg)[(c.row * U + c.unit) * N + lane] = make_float2(myP, myX);
+    }
+}
+
+// ================================================================ pass 2: fold unit aggregates
+// One thread per (row, state).  Forward: carry[u] = state entering unit u, last_state = state after
+// the last unit.  Reverse: carry[u] = adjoint entering unit u from the right.
+template <bool kRev>
+__global__ void __launch_bounds__(128) scan_carry_kernel(const float2* __restrict__ agg, float* __restrict__ carry,
+                                                         float* __restrict__ last_state, const int64_t rows,
+                                                         const int U, const int N) {
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= rows * N) return;
+    const int64_t row = idx / N;
+    const int n = (int)(idx - row * N);
+    const float2* __restrict__ ag = agg + row * U * N + n;
+    float* __restrict__ cr = carry + row * U * N + n;
+    float E = 0.f;
+    constexpr int kBatch = 8;  // independent loads in flight per thread
+    for (int u0 = 0; u0 < U; u0 += kBatch) {
+        float2 v[kBatch];
+#pragma unroll
+        for (int j = 0; j < kBatch; ++j) {
+            const int u = kRev ? U - 1 - (u0 + j) : u0 + j;
+            v[j] = (u0 + j < U) ? __ldg(ag + (int64_t)u * N) : make_float2(1.f, 0.f);
+        }
+#pragma unroll
+        for (int j = 0; j < kBatch; ++j) {
+            if (u0 + j < U) {
+                const int u = kRev ? U - 1 - (u0 + j) : u0 + j;
+                cr[(int64_t)u * N] = E;
+                E = fmaf(v[j].x, E, v[j].y);
+            }
+        }
+    }
+    if (!kRev && last_state) last_state[idx] = E;
+}
+
+// ================================================================ pass 3 (forward)
+template <typename T, bool kVec>
+__global__ void __launch_bounds__(128) scan_fwd_main_kernel(const vv_scan_args a, const int rows_seq) {
+    extern __shared__ float4 smem4[];
+    const int L = a.seqlen, N = a.dstate;
+    float4* tB = smem4;
+    float4* tC = smem4 + N * kSlots;
+    {
+        const RowCoord c0 = row_coord(a, rows_seq, 0);
+        fill_tile<T, kVec>(tB, reinterpret_cast<const T*>(a.Bm) + c0.b * a.B_bs + c0.g * a.B_gs, a.B_ns, N, c0.unit, L);
+        fill_tile<T, kVec>(tC, reinterpret_cast<const T*>(a.Cm) + c0.b * a.C_bs + c0.g * a.C_gs, a.C_ns, N, c0.unit, L);
+    }
+    __syncthreads();
+    const int U = gridDim.x;
+    for (int k = 0; k < rows_seq; ++k) {
+        const RowCoord c = row_coord(a, rows_seq, k);
+        const int lane = c.lane;
+        const int t0 = c.unit * kUnit + lane * kVecElems;
+        const float bias = a.delta_bias ? a.delta_bias[c.d] : 0.f;
+        const float Dv = a.D ? a.D[c.d] : 0.f;
+        float dt[8], du[8], y[8];
+        load_dt<T, kVec>(reinterpret_cast<const T*>(a.delta) + c.b * a.delta_bs + c.d * a.delta_ds, t0, L, bias,
+                         a.delta_softplus != 0, dt);
+        load8<T, kVec>(reinterpret_cast<const T*>(a.u) + c.b * a.u_bs + c.d * a.u_ds, t0, L, du);
+        float sum_dt = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            y[i] = Dv * du[i];
+            du[i] *= dt[i];
+            sum_dt += dt[i];
+        }
+        const float A2_l = lane < N ? a.A[c.d * a.A_ds + lane * a.A_ns] * kLog2e : 0.f;
+        const float E_l = lane < N ? a.chk[(c.row * U + c.unit) * N + lane] : 0.f;
+        for (int n = 0; n < N; ++n) {
+            const float A2 = __shfl_sync(0xffffffffu, A2_l, n);
+            const float E = __shfl_sync(0xffffffffu, E_l, n);
+            float bm[8], cm[8], dec[8];
+            read_tile(tB, n, lane, bm);
+            read_tile(tC, n, lane, cm);
+            float X = 0.f;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                dec[i] = exp2f(dt[i] * A2);
+                bm[i] *= du[i];
+                X = fmaf(dec[i], X, bm[i]);
+            }
+            float P = exp2f(A2 * sum_dt);
+            warp_scan_fwd(P, X, lane);
+            float Pex = __shfl_up_sync(0xffffffffu, P, 1);
+            float Xex = __shfl_up_sync(0xffffffffu, X, 1);
+            if (lane == 0) { Pex = 1.f; Xex = 0.f; }
+            float h = fmaf(Pex, E, Xex);  // state entering this lane's first position
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                h = fmaf(dec[i], h, bm[i]);
+                y[i] = fmaf(cm[i], h, y[i]);
+            }
+        }
+        if (a.out) store8<T, kVec>(reinterpret_cast<T*>(a.out) + c.b * a.out_bs + c.d * a.out_ds, t0, L, y);
+        if (a.z) {
+            float zv[8];
+            load8<T, kVec>(reinterpret_cast<const T*>(a.z) + c.b * a.z_bs + c.d * a.z_ds, t0, L, zv);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) y[i] *= zv[i] * sigmoid_f(zv[i]);
+            store8<T, kVec>(reinterpret_cast<T*>(a.out_z) + c.b * a.outz_bs + c.d * a.outz_ds, t0, L, y);
+        }
+    }
+}
+
+// ================================================================ pass 3 (backward)
+// Gradient formulas (real A, variable B and C): selective_scan_bwd_kernel.cuh:279-295, 439-453.
+template <typename T, bool kVec>
+__global__ void __launch_bounds__(128) scan_bwd_main_kernel(const vv_scan_args a, const int rows_seq) {
+    extern __shared__ float4 smem4[];
+    const int L = a.seqlen, N = a.dstate;
+    const int W = blockDim.x >> 5;
+    float4* tB = smem4;
+    float4* tC = tB + N * kSlots;
+    float4* tdB = tC + N * kSlots;
+    float4* tdC = tdB + N * kSlots;
+    float* s_dA = reinterpret_cast<float*>(tdC + N * kSlots);  // [W][N][kDaPitch]
+    const int U = gridDim.x;
+    {
+        const RowCoord c0 = row_coord(a, rows_seq, 0);
+        fill_tile<T, kVec>(tB, reinterpret_cast<const T*>(a.Bm) + c0.b * a.B_bs + c0.g * a.B_gs, a.B_ns, N, c0.unit, L);
+        fill_tile<T, kVec>(tC, reinterpret_cast<const T*>(a.Cm) + c0.b * a.C_bs + c0.g * a.C_gs, a.C_ns, N, c0.unit, L);
+        for (int idx = threadIdx.x; idx < 2 * N * kSlots; idx += blockDim.x) tdB[idx] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    __syncthreads();
+    for (int k = 0; k < rows_seq; ++k) {
+        const RowCoord c = row_coord(a, rows_seq, k);
+        const int lane = c.lane;
+        const int t0 = c.unit * kUnit + lane * kVecElems;
+        const float bias = a.delta_bias ? a.delta_bias[c.d] : 0.f;
+        const float Dv = a.D ? a.D[c.d] : 0.f;
+        const T* delta_row = reinterpret_cast<const T*>(a.delta) + c.b * a.delta_bs + c.d * a.delta_ds;
+        float dt[8], u[8], g[8], dzf[8];
+        load_dt<T, kVec>(delta_row, t0, L, bias, a.delta_softplus != 0, dt);
+        load8<T, kVec>(reinterpret_cast<const T*>(a.u) + c.b * a.u_bs + c.d * a.u_ds, t0, L, u);
+        load8<T, kVec>(reinterpret_cast<const T*>(a.dout) + c.b * a.dout_bs + c.d * a.dout_ds, t0, L, g);
+        if (a.z) {
+            float zv[8];
+            load8<T, kVec>(reinterpret_cast<const T*>(a.z) + c.b * a.z_bs + c.d * a.z_ds, t0, L, zv);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const float sg = sigmoid_f(zv[i]);
+                dzf[i] = g[i] * sg * (1.f + zv[i] * (1.f - sg));  // dz = dzf * y
+                g[i] *= zv[i] * sg;                                 // grad w.r.t. pre-gate y
+            }
+        }
+        float dt_next = __shfl_down_sync(0xffffffffu, dt[0], 1);
+        if (lane == 31) {
+            const int tn = t0 + kVecElems;
+            dt_next = 0.f;
+            if (tn < L) {
+                const float v = to_f32<T>(delta_row[tn]) + bias;
+                dt_next = a.delta_softplus ? softplus_f(v) : v;
+            }
+        }
+        float sum_dt = 0.f;
+        float y[8], s1[8], ddt[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            sum_dt += dt[i];
+            y[i] = Dv * u[i];
+            s1[i] = 0.f;
+            ddt[i] = 0.f;
+        }
+        const float sum_dt_rev = sum_dt - dt[0] + dt_next;
+        const float A_l = lane < N ? a.A[c.d * a.A_ds + lane * a.A_ns] : 0.f;
+        const float E_l = lane < N ? a.chk[(c.row * U + c.unit) * N + lane] : 0.f;
+        const float R_l = lane < N ? a.radj[(c.row * U + c.unit) * N + lane] : 0.f;
+        float* my_dA = s_dA + c.warp * N * kDaPitch;
+
+        for (int j = 0; j < N; ++j) {
+            // each warp of the CTA works on a different state row between two barriers
+            int n = j + c.warp;
+            if (n >= N) n -= N;
+            const float An = __shfl_sync(0xffffffffu, A_l, n);
+            const float E = __shfl_sync(0xffffffffu, E_l, n);
+            const float R = __shfl_sync(0xffffffffu, R_l, n);
+            const float A2 = An * kLog2e;
+            float bm[8], cm[8], dec[8], hs[8];
+            read_tile(tB, n, lane, bm);
+            read_tile(tC, n, lane, cm);
+            // ---- forward states of the unit, seeded by the checkpoint
+            float X = 0.f;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                dec[i] = exp2f(dt[i] * A2);
+                X = fmaf(dec[i], X, dt[i] * u[i] * bm[i]);
+            }
+            float P = exp2f(A2 * sum_dt);
+            warp_scan_fwd(P, X, lane);
+            float Pex = __shfl_up_sync(0xffffffffu, P, 1);
+            float Xex = __shfl_up_sync(0xffffffffu, X, 1);
+            if (lane == 0) { Pex = 1.f; Xex = 0.f; }
+            float h = fmaf(Pex, E, Xex);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                h = fmaf(dec[i], h, dt[i] * u[i] * bm[i]);
+                hs[i] = h;
+            }
+            // ---- adjoint r_t = g_t C_t + a_{t+1} r_{t+1}, seeded by the reverse carry
+            const float dec_next = exp2f(dt_next * A2);
+            float RX = g[7] * cm[7];
+#pragma unroll
+            for (int i = 6; i >= 0; --i) RX = fmaf(dec[i + 1], RX, g[i] * cm[i]);
+            float RP = exp2f(A2 * sum_dt_rev);
+            warp_scan_rev(RP, RX, lane);
+            float RPex = __shfl_down_sync(0xffffffffu, RP, 1);
+            float RXex = __shfl_down_sync(0xffffffffu, RX, 1);
+            if (lane == 31) { RPex = 1.f; RXex = 0.f; }
+            float r = fmaf(RPex, R, RXex);  // adjoint of the position right after this lane's last one
+            float dA_loc = 0.f;
+            float dBv[8], dCv[8];
+#pragma unroll
+            for (int i = 7; i >= 0; --i) {
+                r = fmaf(i == 7 ? dec_next : dec[i + 1], r, g[i] * cm[i]);
+                const float drive = dt[i] * u[i];
+                const float ah = hs[i] - drive * bm[i];  // = a_t h_{t-1}
+                const float w = r * ah;
+                s1[i] = fmaf(r, bm[i], s1[i]);
+                ddt[i] = fmaf(An, w, ddt[i]);
+                dA_loc = fmaf(dt[i], w, dA_loc);
+                dBv[i] = r * drive;
+                dCv[i] = g[i] * hs[i];
+                y[i] = fmaf(cm[i], hs[i], y[i]);
+            }
+            my_dA[n * kDaPitch + lane] = dA_loc;
+            if (W > 1) __syncthreads();
+            {
+                float4 v = tdB[n * kSlots + lane];
+                v.x += dBv[0]; v.y += dBv[1]; v.z += dBv[2]; v.w += dBv[3];
+                tdB[n * kSlots + lane] = v;
+                v = tdB[n * kSlots + 32 + lane];
+                v.x += dBv[4]; v.y += dBv[5]; v.z += dBv[6]; v.w += dBv[7];
+                tdB[n * kSlots + 32 + lane] = v;
+                v = tdC[n * kSlots + lane];
+                v.x += dCv[0]; v.y += dCv[1]; v.z += dCv[2]; v.w += dCv[3];
+                tdC[n * kSlots + lane] = v;
+                v = tdC[n * kSlots + 32 + lane];
+                v.x += dCv[4]; v.y += dCv[5]; v.z += dCv[6]; v.w += dCv[7];
+                tdC[n * kSlots + 32 + lane] = v;
+            }
+        }
+
+        // ---- per-position outputs of this row
+        float du_o[8], ddt_o[8];
+        float dD_loc = 0.f, dbias_loc = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            du_o[i] = fmaf(Dv, g[i], dt[i] * s1[i]);
+            float dd = fmaf(u[i], s1[i], ddt[i]);
+            // d softplus(v)/dv = sigmoid(v) = 1 - exp(-softplus(v)); dt == 0 marks padding
+            if (a.delta_softplus) dd *= (1.f - __expf(-dt[i]));
+            ddt_o[i] = dd;
+            dbias_loc += (t0 + i < L) ? dd : 0.f;
+            dD_loc = fmaf(g[i], u[i], dD_loc);
+        }
+        store8<T, kVec>(reinterpret_cast<T*>(a.du) + c.b * a.du_bs + c.d * a.du_ds, t0, L, du_o);
+        store8<T, kVec>(reinterpret_cast<T*>(a.ddelta) + c.b * a.ddelta_bs + c.d * a.ddelta_ds, t0, L, ddt_o);
+        if (a.z) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) dzf[i] *= y[i];
+            store8<T, kVec>(reinterpret_cast<T*>(a.dz) + c.b * a.dz_bs + c.d * a.dz_ds, t0, L, dzf);
+        }
+        dD_loc = warp_sum(dD_loc);
+        dbias_loc = warp_sum(dbias_loc);
+        if (lane == 0) {
+            if (a.dD) atomicAdd(a.dD + c.d, dD_loc);
+            if (a.ddelta_bias) atomicAdd(a.ddelta_bias + c.d, dbias_loc);
+        }
+        __syncwarp();
+        if (lane < N) {
+            float s = 0.f;
+#pragma unroll 8
+            for (int i = 0; i < 32; ++i) s += my_dA[lane * kDaPitch + i];
+            atomicAdd(a.dA + c.d * N + lane, s);
+        }
+        __syncwarp();
+    }
+    // ---- the CTA's dB / dC partial sums -> global (fp32, 128-bit reductions)
+    __syncthreads();
+    {
+        const RowCoord c0 = row_coord(a, rows_seq, 0);
+        const int64_t bc_base = ((int64_t)c0.b * a.ngroups + c0.g) * N;
+        for (int idx = threadIdx.x; idx < N * kSlots; idx += blockDim.x) {
+            const int n = idx / kSlots, s = idx - n * kSlots;
+            const int l = s >> 1, half = s & 1;
+            const int t = c0.unit * kUnit + l * kVecElems + half * 4;
+            const float4 vb = tdB[n * kSlots + half * 32 + l];
+            const float4 vc = tdC[n * kSlots + half * 32 + l];
+            float* pb = a.dB + (bc_base + n) * L + t;
+            float* pc = a.dC + (bc_base + n) * L + t;
+            if (kVec) {
+                if (t < L) {
+                    atomicAdd(reinterpret_cast<float4*>(pb), vb);
+                    atomicAdd(reinterpret_cast<float4*>(pc), vc);
+                }
+            } else {
+                const float eb[4] = {vb.x, vb.y, vb.z, vb.w};
+                const float ec[4] = {vc.x, vc.y, vc.z, vc.w};
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    if (t + q < L) {
+                        atomicAdd(pb + q, eb[q]);
+                        atomicAdd(pc + q, ec[q]);
+                    }
+                }
+            }
+        }
+    }
+}
+
+}  // namespace vv

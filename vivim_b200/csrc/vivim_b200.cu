@@ -1,0 +1,266 @@
+// vivim_b200.cu -- C ABI (include/vivim_b200.h) and launch logic for the sm_100a kernels.
+// Argument checks mirror the reference shims' TORCH_CHECKs
+// (causal-conv1d/csrc/causal_conv1d.cpp:130-268, mamba/csrc/selective_scan/selective_scan.cpp:226-492).
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+
+#include "../../include/vivim_b200.h"
+#include "conv1d.cuh"
+#include "scan.cuh"
+
+namespace {
+
+thread_local char g_err[512] = "";
+thread_local int g_launches = 0;
+thread_local int g_pass_mask = 7;
+
+int fail(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+int elem_size(int dtype) { return dtype == VV_F32 ? 4 : 2; }
+bool valid_dtype(int dtype) { return dtype == VV_F32 || dtype == VV_F16 || dtype == VV_BF16; }
+
+// 128-bit access is legal for a (.., L) tensor when its base and every row start are 16-byte aligned
+bool vec_ok(const void* p, int es, std::initializer_list<int64_t> strides) {
+    if (p == nullptr) return true;
+    if (reinterpret_cast<uintptr_t>(p) % 16 != 0) return false;
+    for (int64_t s : strides)
+        if ((s * es) % 16 != 0) return false;
+    return true;
+}
+bool elem_aligned(const void* p, int es) { return p == nullptr || reinterpret_cast<uintptr_t>(p) % es == 0; }
+
+int check_launch(const char* what) {
+    const cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail((int)e, "%s: %s", what, cudaGetErrorString(e));
+    ++g_launches;
+    return VV_OK;
+}
+
+int env_int(const char* name, int dflt) {
+    const char* v = getenv(name);
+    return (v && *v) ? atoi(v) : dflt;
+}
+
+// ---------------------------------------------------------------- conv1d dispatch
+template <typename T, bool kBwd>
+int launch_conv_t(const vv_conv1d_args& a, bool vec, cudaStream_t st) {
+    const dim3 grid((unsigned)((int64_t)a.batch * a.dim), (unsigned)((a.seqlen + vv::kConvTile - 1) / vv::kConvTile));
+    const dim3 block(vv::kConvThreads);
+#define VV_CONV_LAUNCH(SILU, VEC)                                                    \
+    do {                                                                             \
+        if (kBwd) vv::conv1d_bwd_kernel<T, SILU, VEC><<<grid, block, 0, st>>>(a);    \
+        else vv::conv1d_fwd_kernel<T, SILU, VEC><<<grid, block, 0, st>>>(a);         \
+    } while (0)
+    if (a.silu) { if (vec) VV_CONV_LAUNCH(true, true); else VV_CONV_LAUNCH(true, false); }
+    else        { if (vec) VV_CONV_LAUNCH(false, true); else VV_CONV_LAUNCH(false, false); }
+#undef VV_CONV_LAUNCH
+    return check_launch(kBwd ? "conv1d_bwd_kernel" : "conv1d_fwd_kernel");
+}
+
+template <bool kBwd>
+int launch_conv(const vv_conv1d_args* a, void* stream) {
+    g_launches = 0;
+    if (!a) return fail(VV_ERR_BAD_ARG, "conv1d: null args");
+    if (!a->x || !a->weight) return fail(VV_ERR_BAD_ARG, "conv1d: x and weight are required");
+    if (!kBwd && !a->out) return fail(VV_ERR_BAD_ARG, "conv1d_fwd: out is required");
+    if (kBwd && (!a->dout || !a->dx || !a->dweight)) return fail(VV_ERR_BAD_ARG, "conv1d_bwd: dout, dx, dweight are required");
+    if (kBwd && a->bias && !a->dbias) return fail(VV_ERR_BAD_ARG, "conv1d_bwd: dbias is required when bias is given");
+    if (a->batch <= 0 || a->dim <= 0 || a->seqlen <= 0) return fail(VV_ERR_BAD_ARG, "conv1d: sizes must be positive");
+    if (!valid_dtype(a->io_dtype) || !valid_dtype(a->w_dtype)) return fail(VV_ERR_BAD_ARG, "conv1d: dtype must be fp32, fp16 or bf16");
+    if (a->width < 2 || a->width > 4) return fail(VV_ERR_UNSUPPORTED, "causal_conv1d only supports width between 2 and 4");
+    const int es = elem_size(a->io_dtype);
+    if (!elem_aligned(a->x, es) || !elem_aligned(a->out, es) || !elem_aligned(a->dout, es) || !elem_aligned(a->dx, es))
+        return fail(VV_ERR_ALIGN, "conv1d: tensor not aligned to its element size");
+    bool vec = a->seqlen % 8 == 0 && vec_ok(a->x, es, {a->x_bs, a->x_ds});
+    if (kBwd) vec = vec && vec_ok(a->dout, es, {a->dout_bs, a->dout_ds}) && vec_ok(a->dx, es, {a->dx_bs, a->dx_ds});
+    else vec = vec && vec_ok(a->out, es, {a->out_bs, a->out_ds});
+    if (env_int("VV_FORCE_SCALAR_IO", 0)) vec = false;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    switch (a->io_dtype) {
+        case VV_F32: return launch_conv_t<float, kBwd>(*a, vec, st);
+        case VV_F16: return launch_conv_t<__half, kBwd>(*a, vec, st);
+        default: return launch_conv_t<__nv_bfloat16, kBwd>(*a, vec, st);
+    }
+}
+
+// ---------------------------------------------------------------- scan dispatch
+struct ScanPlan {
+    int W;         // warps (= channels processed concurrently) per CTA
+    int rows_seq;  // channels each warp walks one after another
+    int units;
+};
+
+ScanPlan plan_scan(const vv_scan_args& a) {
+    ScanPlan p;
+    p.units = vv_scan_num_units(a.seqlen);
+    const int dpg = a.dim / a.ngroups;
+    p.W = 1;
+    for (int w : {4, 2}) {
+        if (w <= a.dstate && dpg % w == 0) { p.W = w; break; }
+    }
+    // Largest run of channels per warp that still leaves >= 8 CTAs per SM (148 SMs) in the grid.
+    const int64_t ctas_at_1 = (int64_t)a.batch * p.units * (a.dim / p.W);
+    p.rows_seq = 1;
+    for (int r : {8, 4, 2}) {
+        if ((dpg / p.W) % r == 0 && ctas_at_1 / r >= 8 * 148) { p.rows_seq = r; break; }
+    }
+    const int forced = env_int("VV_SCAN_ROWS_SEQ", 0);
+    if (forced > 0 && (dpg / p.W) % forced == 0) p.rows_seq = forced;
+    return p;
+}
+
+int check_scan_common(const vv_scan_args* a, bool bwd) {
+    if (!a) return fail(VV_ERR_BAD_ARG, "scan: null args");
+    if (!a->u || !a->delta || !a->A || !a->Bm || !a->Cm) return fail(VV_ERR_BAD_ARG, "scan: u, delta, A, B, C are required");
+    if (!a->agg || !a->chk) return fail(VV_ERR_BAD_ARG, "scan: agg and chk workspaces are required");
+    if (a->batch <= 0 || a->dim <= 0 || a->seqlen <= 0 || a->dstate <= 0 || a->ngroups <= 0)
+        return fail(VV_ERR_BAD_ARG, "scan: sizes must be positive");
+    if (a->dim % a->ngroups != 0) return fail(VV_ERR_BAD_ARG, "scan: ngroups must divide dim");
+    if (a->dstate > 256) return fail(VV_ERR_BAD_ARG, "selective_scan only supports state dimension <= 256");
+    if (a->dstate > vv::kMaxState)
+        return fail(VV_ERR_UNSUPPORTED, "scan: this build serves dstate <= %d (got %d)", vv::kMaxState, a->dstate);
+    if (!valid_dtype(a->io_dtype)) return fail(VV_ERR_BAD_ARG, "scan: dtype must be fp32, fp16 or bf16");
+    if (a->batch > 65535) return fail(VV_ERR_UNSUPPORTED, "scan: batch > 65535");
+    if (!bwd) {
+        if (a->z && !a->out_z) return fail(VV_ERR_BAD_ARG, "scan_fwd: out_z is required when z is given");
+        if (!a->z && !a->out) return fail(VV_ERR_BAD_ARG, "scan_fwd: out is required when z is absent");
+    } else {
+        if (!a->dout || !a->du || !a->ddelta || !a->dA || !a->dB || !a->dC || !a->radj)
+            return fail(VV_ERR_BAD_ARG, "scan_bwd: dout, du, ddelta, dA, dB, dC, radj are required");
+        if (a->z && !a->dz) return fail(VV_ERR_BAD_ARG, "scan_bwd: dz is required when z is given");
+        if (a->D && !a->dD) return fail(VV_ERR_BAD_ARG, "scan_bwd: dD is required when D is given");
+        if (a->delta_bias && !a->ddelta_bias) return fail(VV_ERR_BAD_ARG, "scan_bwd: ddelta_bias is required when delta_bias is given");
+    }
+    const int es = elem_size(a->io_dtype);
+    const void* ptrs[] = {a->u, a->delta, a->Bm, a->Cm, a->z, a->out, a->out_z, a->dout, a->du, a->ddelta, a->dz};
+    for (const void* p : ptrs)
+        if (!elem_aligned(p, es)) return fail(VV_ERR_ALIGN, "scan: tensor not aligned to its element size");
+    return VV_OK;
+}
+
+bool scan_vec_ok(const vv_scan_args& a, bool bwd) {
+    const int es = elem_size(a.io_dtype);
+    bool v = a.seqlen % 8 == 0;
+    v = v && vec_ok(a.u, es, {a.u_bs, a.u_ds}) && vec_ok(a.delta, es, {a.delta_bs, a.delta_ds});
+    v = v && vec_ok(a.Bm, es, {a.B_bs, a.B_gs, a.B_ns}) && vec_ok(a.Cm, es, {a.C_bs, a.C_gs, a.C_ns});
+    v = v && vec_ok(a.z, es, {a.z_bs, a.z_ds});
+    if (!bwd) {
+        v = v && vec_ok(a.out, es, {a.out_bs, a.out_ds}) && vec_ok(a.out_z, es, {a.outz_bs, a.outz_ds});
+    } else {
+        v = v && vec_ok(a.dout, es, {a.dout_bs, a.dout_ds}) && vec_ok(a.du, es, {a.du_bs, a.du_ds});
+        v = v && vec_ok(a.ddelta, es, {a.ddelta_bs, a.ddelta_ds}) && vec_ok(a.dz, es, {a.dz_bs, a.dz_ds});
+        v = v && vec_ok(a.dB, 4, {}) && vec_ok(a.dC, 4, {});
+    }
+    if (env_int("VV_FORCE_SCALAR_IO", 0)) v = false;
+    return v;
+}
+
+template <typename K>
+int set_smem(K kernel, size_t bytes) {
+    if (bytes <= 48 * 1024) return VV_OK;
+    const cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (e != cudaSuccess) return fail((int)e, "cudaFuncSetAttribute(%zu B): %s", bytes, cudaGetErrorString(e));
+    return VV_OK;
+}
+
+template <typename T, bool kVec>
+int scan_fwd_t(const vv_scan_args& a, cudaStream_t st) {
+    const ScanPlan p = plan_scan(a);
+    const dim3 grid(p.units, a.dim / (p.W * p.rows_seq), a.batch);
+    const dim3 block(p.W * 32);
+    const size_t tile = (size_t)a.dstate * vv::kSlots * sizeof(float4);
+    const int64_t rows = (int64_t)a.batch * a.dim;
+    int rc;
+    if (g_pass_mask & 1) {
+        vv::scan_agg_kernel<T, kVec, false><<<grid, block, tile, st>>>(a, p.rows_seq);
+        if ((rc = check_launch("scan_agg_kernel<fwd>")) != VV_OK) return rc;
+    }
+    if (g_pass_mask & 2) {
+        const int64_t chains = rows * a.dstate;
+        vv::scan_carry_kernel<false><<<(unsigned)((chains + 127) / 128), 128, 0, st>>>(
+            reinterpret_cast<const float2*>(a.agg), a.chk, a.last_state, rows, p.units, a.dstate);
+        if ((rc = check_launch("scan_carry_kernel<fwd>")) != VV_OK) return rc;
+    }
+    if (g_pass_mask & 4) {
+        if ((rc = set_smem(vv::scan_fwd_main_kernel<T, kVec>, 2 * tile)) != VV_OK) return rc;
+        vv::scan_fwd_main_kernel<T, kVec><<<grid, block, 2 * tile, st>>>(a, p.rows_seq);
+        if ((rc = check_launch("scan_fwd_main_kernel")) != VV_OK) return rc;
+    }
+    return VV_OK;
+}
+
+template <typename T, bool kVec>
+int scan_bwd_t(const vv_scan_args& a, cudaStream_t st) {
+    const ScanPlan p = plan_scan(a);
+    const dim3 grid(p.units, a.dim / (p.W * p.rows_seq), a.batch);
+    const dim3 block(p.W * 32);
+    const size_t tile = (size_t)a.dstate * vv::kSlots * sizeof(float4);
+    const int64_t rows = (int64_t)a.batch * a.dim;
+    int rc;
+    if (g_pass_mask & 1) {
+        vv::scan_agg_kernel<T, kVec, true><<<grid, block, tile, st>>>(a, p.rows_seq);
+        if ((rc = check_launch("scan_agg_kernel<rev>")) != VV_OK) return rc;
+    }
+    if (g_pass_mask & 2) {
+        const int64_t chains = rows * a.dstate;
+        vv::scan_carry_kernel<true><<<(unsigned)((chains + 127) / 128), 128, 0, st>>>(
+            reinterpret_cast<const float2*>(a.agg), a.radj, nullptr, rows, p.units, a.dstate);
+        if ((rc = check_launch("scan_carry_kernel<rev>")) != VV_OK) return rc;
+    }
+    if (g_pass_mask & 4) {
+        const size_t smem = 4 * tile + (size_t)p.W * a.dstate * vv::kDaPitch * sizeof(float);
+        if ((rc = set_smem(vv::scan_bwd_main_kernel<T, kVec>, smem)) != VV_OK) return rc;
+        vv::scan_bwd_main_kernel<T, kVec><<<grid, block, smem, st>>>(a, p.rows_seq);
+        if ((rc = check_launch("scan_bwd_main_kernel")) != VV_OK) return rc;
+    }
+    return VV_OK;
+}
+
+template <bool kBwd>
+int launch_scan(const vv_scan_args* a, void* stream) {
+    g_launches = 0;
+    const int rc = check_scan_common(a, kBwd);
+    if (rc != VV_OK) return rc;
+    const bool vec = scan_vec_ok(*a, kBwd);
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+#define VV_SCAN_CALL(T)                                                                      \
+    do {                                                                                     \
+        if (kBwd) return vec ? scan_bwd_t<T, true>(*a, st) : scan_bwd_t<T, false>(*a, st);   \
+        return vec ? scan_fwd_t<T, true>(*a, st) : scan_fwd_t<T, false>(*a, st);             \
+    } while (0)
+    switch (a->io_dtype) {
+        case VV_F32: VV_SCAN_CALL(float);
+        case VV_F16: VV_SCAN_CALL(__half);
+        default: VV_SCAN_CALL(__nv_bfloat16);
+    }
+#undef VV_SCAN_CALL
+}
+
+}  // namespace
+
+extern "C" {
+
+int vv_version(void) { return VV_VERSION; }
+const char* vv_last_error(void) { return g_err; }
+int vv_last_launch_count(void) { return g_launches; }
+int vv_scan_set_pass_mask(int mask) {
+    const int prev = g_pass_mask;
+    g_pass_mask = mask & 7;
+    return prev;
+}
+int vv_scan_num_units(int seqlen) { return seqlen <= 0 ? 0 : (seqlen + VV_SCAN_UNIT - 1) / VV_SCAN_UNIT; }
+
+int vv_conv1d_fwd(const vv_conv1d_args* a, void* stream) { return launch_conv<false>(a, stream); }
+int vv_conv1d_bwd(const vv_conv1d_args* a, void* stream) { return launch_conv<true>(a, stream); }
+int vv_scan_fwd(const vv_scan_args* a, void* stream) { return launch_scan<false>(a, stream); }
+int vv_scan_bwd(const vv_scan_args* a, void* stream) { return launch_scan<true>(a, stream); }
+
+}  // extern "C"

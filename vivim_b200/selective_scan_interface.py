@@ -1,0 +1,315 @@
+"""Drop-in for ``mamba_ssm.ops.selective_scan_interface`` of the reference
+(mamba/mamba_ssm/ops/selective_scan_interface.py): ``selective_scan_fn``, ``mamba_inner_fn``,
+``mamba_inner_fn_no_out_proj``, ``bimamba_inner_fn`` and the ``*_ref`` statements, with the same
+signatures.  The conv and scan run in the sm_100a kernels of libvivim_b200.so; the x_proj / dt_proj /
+out_proj GEMMs stay torch (cuBLAS) calls, as in the reference.
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn.functional as F
+
+from . import causal_conv1d_cuda, selective_scan_cuda
+from .causal_conv1d_interface import causal_conv1d_fn
+
+_fwd_amp = torch.amp.custom_fwd(device_type="cuda")
+_bwd_amp = torch.amp.custom_bwd(device_type="cuda")
+
+
+def _last_contig(t):
+    return t if t is None or t.stride(-1) == 1 else t.contiguous()
+
+
+def _as_groups(M, u, A, name):
+    """B / C as (batch, groups, dstate, seqlen).  Returns (tensor, kind) with kind in
+    'bnl' (was 3-D variable), 'bgnl' (4-D variable) or 'dn' (constant (dim, dstate))."""
+    if A.is_complex():
+        raise NotImplementedError("complex A is not served by the B200 kernels")
+    if M.dim() == 4:
+        return _last_contig(M), "bgnl"
+    if M.dim() == 3:
+        return _last_contig(M).unsqueeze(1), "bnl"
+    if M.dim() == 2:
+        # constant B/C (dim, dstate): one group per channel, broadcast over batch and time.
+        # Correct but slow; Vivim always uses input-dependent B and C.
+        batch, dim, seqlen = u.shape
+        return M.to(u.dtype)[None, :, :, None].expand(batch, dim, M.shape[1], seqlen).contiguous(), "dn"
+    raise RuntimeError(f"selective_scan: {name} must have 2, 3 or 4 dimensions")
+
+
+def _ungroup_grad(dM, kind):
+    if kind == "bnl":
+        return dM.squeeze(1)
+    if kind == "dn":
+        return dM.float().sum(dim=(0, 3))   # autograd casts to the parameter's dtype
+    return dM
+
+
+class SelectiveScanFn(torch.autograd.Function):
+    """reference: selective_scan_interface.py:14-74"""
+
+    @staticmethod
+    def forward(ctx, u, delta, A, B, C, D=None, z=None, delta_bias=None, delta_softplus=False,
+                return_last_state=False):
+        u, delta, z = _last_contig(u), _last_contig(delta), _last_contig(z)
+        if D is not None:
+            D = D.contiguous()
+        Bg, ctx.kind_B = _as_groups(B, u, A, "B")
+        Cg, ctx.kind_C = _as_groups(C, u, A, "C")
+        out, chk, last_state, *rest = selective_scan_cuda.fwd(
+            u, delta, A, Bg, Cg, D, z, delta_bias, delta_softplus, want_out=z is None)
+        ctx.delta_softplus = delta_softplus
+        ctx.has_z = z is not None
+        ctx.save_for_backward(u, delta, A, Bg, Cg, D, z, delta_bias, chk)
+        result = rest[0] if ctx.has_z else out
+        if return_last_state:
+            ctx.mark_non_differentiable(last_state)
+            return result, last_state
+        return result
+
+    @staticmethod
+    def backward(ctx, dout, *unused):
+        u, delta, A, Bg, Cg, D, z, delta_bias, chk = ctx.saved_tensors
+        dout = _last_contig(dout)
+        du, ddelta, dA, dB, dC, dD, ddelta_bias, *rest = selective_scan_cuda.bwd(
+            u, delta, A, Bg, Cg, D, z, delta_bias, dout, chk, None, ctx.delta_softplus)
+        dz = rest[0] if ctx.has_z else None
+        return (du, ddelta, dA, _ungroup_grad(dB, ctx.kind_B), _ungroup_grad(dC, ctx.kind_C),
+                dD, dz, ddelta_bias, None, None)
+
+
+def selective_scan_fn(u, delta, A, B, C, D=None, z=None, delta_bias=None, delta_softplus=False,
+                      return_last_state=False):
+    """If ``return_last_state`` is True returns (out, last_state) with last_state (batch, dim, dstate);
+    the gradient of last_state is not propagated.  reference: selective_scan_interface.py:77-83"""
+    return SelectiveScanFn.apply(u, delta, A, B, C, D, z, delta_bias, delta_softplus, return_last_state)
+
+
+def selective_scan_ref(u, delta, A, B, C, D=None, z=None, delta_bias=None, delta_softplus=False,
+                       return_last_state=False):
+    """Pure-torch statement of the op's semantics for real A (reference:
+    selective_scan_interface.py:86-152).  Kept importable for API parity; never called by the
+    product path.  Sequential in time; O(L) time, fp32 state."""
+    if A.is_complex():
+        raise NotImplementedError("selective_scan_ref here covers real A only")
+    dt = delta.float()
+    if delta_bias is not None:
+        dt = dt + delta_bias.float()[:, None]
+    if delta_softplus:
+        dt = F.softplus(dt)
+    uf = u.float()
+    batch, dim, seqlen = uf.shape
+
+    def per_channel(M):  # -> (batch, dim, dstate, seqlen)
+        M = M.float()
+        if M.dim() == 2:
+            return M[None, :, :, None].expand(batch, -1, -1, seqlen)
+        if M.dim() == 3:
+            return M[:, None].expand(-1, dim, -1, -1)
+        return M.repeat_interleave(dim // M.shape[1], dim=1)
+
+    Bf, Cf = per_channel(B), per_channel(C)
+    h = uf.new_zeros(batch, dim, A.shape[1])
+    ys = []
+    for t in range(seqlen):
+        h = torch.exp(dt[:, :, t, None] * A) * h + (dt[:, :, t] * uf[:, :, t])[..., None] * Bf[..., t]
+        ys.append((h * Cf[..., t]).sum(-1))
+    y = torch.stack(ys, dim=2)
+    if D is not None:
+        y = y + uf * D[:, None]
+    if z is not None:
+        y = y * F.silu(z.float())
+    y = y.to(u.dtype)
+    return (y, h) if return_last_state else y
+
+
+# ---------------------------------------------------------------------------------------------
+# fused inner block: conv1d+SiLU -> x_proj -> dt_proj -> selective scan (gated by z) [-> out_proj]
+# ---------------------------------------------------------------------------------------------
+
+def _project(conv_out, x_proj_weight, delta_proj_weight, A, B, C, B_proj_bias, C_proj_bias):
+    """x_dbl, delta, B, C from the conv output (reference: selective_scan_interface.py:181-210)."""
+    batch, _, L = conv_out.shape
+    rank = delta_proj_weight.shape[1]
+    dstate = A.shape[-1]
+    x_dbl = F.linear(conv_out.transpose(1, 2).reshape(batch * L, -1), x_proj_weight)   # (b l, R+2N)
+    delta = (delta_proj_weight @ x_dbl[:, :rank].t()).view(-1, batch, L).transpose(0, 1)  # (b, d, l) view
+
+    def pick(M, lo, hi, proj_bias, name):
+        if M is not None:   # caller-provided B / C: not input-dependent through x_proj
+            return _as_groups(M, conv_out, A, name)
+        cols = x_dbl[:, lo:hi]
+        if proj_bias is not None:
+            cols = cols + proj_bias.to(cols.dtype)
+        return cols.reshape(batch, L, dstate).transpose(1, 2).contiguous().unsqueeze(1), "proj"  # (b,1,n,l)
+
+    Bm, kind_B = pick(B, rank, rank + dstate, B_proj_bias, "B")
+    Cm, kind_C = pick(C, x_dbl.shape[1] - dstate, x_dbl.shape[1], C_proj_bias, "C")
+    return x_dbl, delta, Bm, Cm, kind_B, kind_C
+
+
+def _delta_from(x_dbl, delta_proj_weight, batch, L):
+    rank = delta_proj_weight.shape[1]
+    return (delta_proj_weight @ x_dbl[:, :rank].t()).view(-1, batch, L).transpose(0, 1)
+
+
+class _MambaInner(torch.autograd.Function):
+    """One Function behind mamba_inner_fn (with out_proj) and mamba_inner_fn_no_out_proj.
+    reference: MambaInnerFnNoOutProj (selective_scan_interface.py:155-289) and MambaInnerFn
+    (:292-434).  checkpoint_lvl=1 semantics: conv output and delta are recomputed in backward."""
+
+    @staticmethod
+    @_fwd_amp
+    def forward(ctx, xz, conv1d_weight, conv1d_bias, x_proj_weight, delta_proj_weight,
+                out_proj_weight, out_proj_bias, A, B, C, D, delta_bias, B_proj_bias, C_proj_bias,
+                delta_softplus, has_out_proj, checkpoint_lvl):
+        assert checkpoint_lvl in (0, 1)
+        if A.is_complex():
+            raise NotImplementedError("complex A is not served by the B200 kernels")
+        if torch.is_autocast_enabled("cuda"):
+            amp = torch.get_autocast_dtype("cuda")
+            x_proj_weight = x_proj_weight.to(amp)
+            delta_proj_weight = delta_proj_weight.to(amp)
+            if has_out_proj:
+                out_proj_weight = out_proj_weight.to(amp)
+                out_proj_bias = out_proj_bias.to(amp) if out_proj_bias is not None else None
+        xz = _last_contig(xz)
+        conv_w = conv1d_weight.squeeze(1)                      # (d, 1, w) -> (d, w)
+        conv_b = conv1d_bias.contiguous() if conv1d_bias is not None else None
+        x, z = xz.chunk(2, dim=1)                              # views: batch stride 2*D*L
+        conv_out = causal_conv1d_cuda.causal_conv1d_fwd(x, conv_w, conv_b, True)
+        x_dbl, delta, Bm, Cm, kind_B, kind_C = _project(
+            conv_out, x_proj_weight, delta_proj_weight, A, B, C, B_proj_bias, C_proj_bias)
+        if D is not None:
+            D = D.contiguous()
+        _, chk, _, out_z = selective_scan_cuda.fwd(
+            conv_out, delta, A, Bm, Cm, D, z, delta_bias, delta_softplus, want_out=False)
+        ctx.delta_softplus = delta_softplus
+        ctx.has_out_proj = has_out_proj
+        ctx.kind_B, ctx.kind_C = kind_B, kind_C
+        ctx.has_B_bias, ctx.has_C_bias = B_proj_bias is not None, C_proj_bias is not None
+        ctx.has_out_bias = out_proj_bias is not None
+        ctx.recompute = checkpoint_lvl >= 1
+        ctx.save_for_backward(xz, conv_w, conv_b, x_dbl, x_proj_weight, delta_proj_weight,
+                              out_proj_weight if has_out_proj else None,
+                              None if ctx.recompute else conv_out, None if ctx.recompute else delta,
+                              A, Bm, Cm, D, delta_bias, chk, out_z if has_out_proj else None)
+        if has_out_proj:
+            return F.linear(out_z.transpose(1, 2), out_proj_weight, out_proj_bias)   # (b, l, e)
+        return out_z                                                                   # (b, d, l)
+
+    @staticmethod
+    @_bwd_amp
+    def backward(ctx, dout):
+        (xz, conv_w, conv_b, x_dbl, x_proj_weight, delta_proj_weight, out_proj_weight,
+         conv_out, delta, A, Bm, Cm, D, delta_bias, chk, out_z) = ctx.saved_tensors
+        batch, two_d, L = xz.shape
+        dim = two_d // 2
+        rank = delta_proj_weight.shape[1]
+        dstate = A.shape[-1]
+        x, z = xz.chunk(2, dim=1)
+        if ctx.recompute:
+            conv_out = causal_conv1d_cuda.causal_conv1d_fwd(x, conv_w, conv_b, True)
+            delta = _delta_from(x_dbl, delta_proj_weight, batch, L)
+        dout_proj_weight = dout_proj_bias = None
+        if ctx.has_out_proj:
+            dflat = dout.reshape(batch * L, -1)                                      # (b l, e)
+            dout_y = (dflat @ out_proj_weight).view(batch, L, dim).transpose(1, 2).contiguous()
+            dout_proj_weight = dflat.t() @ out_z.transpose(1, 2).reshape(batch * L, dim)
+            dout_proj_bias = dflat.sum(0) if ctx.has_out_bias else None
+        else:
+            dout_y = _last_contig(dout)
+        # dx and dz are written next to each other so that no torch.cat is needed
+        dxz = torch.empty_like(xz)
+        dx, dz = dxz.chunk(2, dim=1)
+        dconv, ddelta, dA, dB, dC, dD, ddelta_bias, dz = selective_scan_cuda.bwd(
+            conv_out, delta, A, Bm, Cm, D, z, delta_bias, dout_y, chk, dz, ctx.delta_softplus)
+        dx_dbl = torch.empty_like(x_dbl)
+        dB_out = dC_out = dB_proj_bias = dC_proj_bias = None
+        if ctx.kind_B == "proj":
+            dBf = dB.squeeze(1).transpose(1, 2).reshape(batch * L, dstate)
+            dB_proj_bias = dBf.sum(0) if ctx.has_B_bias else None
+            dx_dbl[:, rank:rank + dstate] = dBf
+        else:
+            dB_out = _ungroup_grad(dB, ctx.kind_B)
+            dx_dbl[:, rank:rank + dstate] = 0
+        if ctx.kind_C == "proj":
+            dCf = dC.squeeze(1).transpose(1, 2).reshape(batch * L, dstate)
+            dC_proj_bias = dCf.sum(0) if ctx.has_C_bias else None
+            dx_dbl[:, -dstate:] = dCf
+        else:
+            dC_out = _ungroup_grad(dC, ctx.kind_C)
+            dx_dbl[:, -dstate:] = 0
+        ddelta_f = ddelta.transpose(0, 1).reshape(dim, batch * L)                     # (d, b l)
+        ddelta_proj_weight = ddelta_f @ x_dbl[:, :rank]
+        dx_dbl[:, :rank] = ddelta_f.t() @ delta_proj_weight
+        conv_flat = conv_out.transpose(1, 2).reshape(batch * L, dim)                  # (b l, d)
+        dx_proj_weight = dx_dbl.t() @ conv_flat
+        # dconv (b, d, l) += (dx_dbl @ x_proj_weight) laid out as (b, l, d)
+        dconv = dconv + (dx_dbl @ x_proj_weight).view(batch, L, dim).transpose(1, 2)
+        dx, dconv_w, dconv_b = causal_conv1d_cuda.causal_conv1d_bwd(x, conv_w, conv_b, dconv, dx, True)
+        return (dxz, dconv_w.unsqueeze(1), dconv_b, dx_proj_weight, ddelta_proj_weight,
+                dout_proj_weight, dout_proj_bias, dA, dB_out, dC_out, dD, ddelta_bias,
+                dB_proj_bias, dC_proj_bias, None, None, None)
+
+
+def mamba_inner_fn(xz, conv1d_weight, conv1d_bias, x_proj_weight, delta_proj_weight,
+                   out_proj_weight, out_proj_bias, A, B=None, C=None, D=None, delta_bias=None,
+                   B_proj_bias=None, C_proj_bias=None, delta_softplus=True):
+    """reference: selective_scan_interface.py:606-614.  Returns (batch, seqlen, d_model)."""
+    return _MambaInner.apply(xz, conv1d_weight, conv1d_bias, x_proj_weight, delta_proj_weight,
+                             out_proj_weight, out_proj_bias, A, B, C, D, delta_bias, B_proj_bias,
+                             C_proj_bias, delta_softplus, True, 1)
+
+
+def mamba_inner_fn_no_out_proj(xz, conv1d_weight, conv1d_bias, x_proj_weight, delta_proj_weight,
+                               A, B=None, C=None, D=None, delta_bias=None, B_proj_bias=None,
+                               C_proj_bias=None, delta_softplus=True):
+    """What Vivim's Mamba(bimamba_type="v3") calls three times per layer
+    (reference: selective_scan_interface.py:627-633; caller mamba_simple.py:217-260).
+    Returns the gated scan output (batch, d_inner, seqlen)."""
+    return _MambaInner.apply(xz, conv1d_weight, conv1d_bias, x_proj_weight, delta_proj_weight,
+                             None, None, A, B, C, D, delta_bias, B_proj_bias, C_proj_bias,
+                             delta_softplus, False, 1)
+
+
+def _inner_pre(xz, conv1d_weight, conv1d_bias, x_proj_weight, delta_proj_weight, A, B, C,
+               B_proj_bias, C_proj_bias, conv_fn):
+    x, z = xz.chunk(2, dim=1)
+    xc = conv_fn(x, conv1d_weight.squeeze(1), conv1d_bias, "silu")
+    _, delta, Bm, Cm, _, _ = _project(xc, x_proj_weight, delta_proj_weight, A, B, C, B_proj_bias, C_proj_bias)
+    return xc, z, delta, Bm, Cm
+
+
+def bimamba_inner_fn(xz, conv1d_weight, conv1d_bias, x_proj_weight, delta_proj_weight,
+                     out_proj_weight, out_proj_bias, A, A_b, B=None, C=None, D=None, delta_bias=None,
+                     B_proj_bias=None, C_proj_bias=None, delta_softplus=True):
+    """Shared conv / projections, one scan left-to-right with A and one right-to-left with A_b, summed,
+    then out_proj (reference: BiMambaInnerFn, selective_scan_interface.py:437-603, 616-624).
+    Exported for API parity (mamba_ssm/__init__.py:3); Vivim never calls it.  Composed from the
+    autograd ops above rather than hand-fused."""
+    xc, z, delta, Bm, Cm = _inner_pre(xz, conv1d_weight, conv1d_bias, x_proj_weight, delta_proj_weight,
+                                      A, B, C, B_proj_bias, C_proj_bias, causal_conv1d_fn)
+    y = selective_scan_fn(xc, delta, A, Bm, Cm, D, z=z, delta_bias=delta_bias, delta_softplus=delta_softplus)
+    y_b = selective_scan_fn(xc.flip([-1]), delta.flip([-1]), A_b, Bm.flip([-1]), Cm.flip([-1]), D,
+                            z=z.flip([-1]), delta_bias=delta_bias, delta_softplus=delta_softplus)
+    return F.linear((y + y_b.flip([-1])).transpose(1, 2), out_proj_weight, out_proj_bias)
+
+
+def mamba_inner_ref(xz, conv1d_weight, conv1d_bias, x_proj_weight, delta_proj_weight,
+                    out_proj_weight, out_proj_bias, A, B=None, C=None, D=None, delta_bias=None,
+                    B_proj_bias=None, C_proj_bias=None, delta_softplus=True):
+    """Unfused composition of the public ops (reference: selective_scan_interface.py:636-670)."""
+    xc, z, delta, Bm, Cm = _inner_pre(xz, conv1d_weight, conv1d_bias, x_proj_weight, delta_proj_weight,
+                                      A, B, C, B_proj_bias, C_proj_bias, causal_conv1d_fn)
+    y = selective_scan_fn(xc, delta, A, Bm, Cm, D, z=z, delta_bias=delta_bias, delta_softplus=True)
+    return F.linear(y.transpose(1, 2), out_proj_weight, out_proj_bias)
+
+
+def bimamba_inner_ref(xz, conv1d_weight, conv1d_bias, x_proj_weight, delta_proj_weight,
+                      out_proj_weight, out_proj_bias, A, A_b, B=None, C=None, D=None, delta_bias=None,
+                      B_proj_bias=None, C_proj_bias=None, delta_softplus=True):
+    """reference: selective_scan_interface.py:673-709 (same composition as bimamba_inner_fn here)."""
+    return bimamba_inner_fn(xz, conv1d_weight, conv1d_bias, x_proj_weight, delta_proj_weight,
+                            out_proj_weight, out_proj_bias, A, A_b, B, C, D, delta_bias,
+                            B_proj_bias, C_proj_bias, True)
