@@ -68,7 +68,7 @@ class ClockSampler:
     def __enter__(self):
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--id={self.idx}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50"],
+                ["nvidia-smi", f"--id={self.idx}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20"],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thr = threading.Thread(target=self._read, daemon=True)
             self.thr.start()
@@ -78,7 +78,16 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.perf_counter(), [c.strip() for c in line.split(",")]))
+
+    def wait_first_sample(self, timeout=3.0):
+        t0 = time.perf_counter()
+        while self.proc is not None and not self.rows and time.perf_counter() - t0 < timeout:
+            time.sleep(0.01)
+
+    def mark(self):
+        """samples taken from now on count as 'under load'"""
+        self.t_mark = time.perf_counter()
 
     def __exit__(self, *exc):
         if self.proc is not None:
@@ -93,7 +102,10 @@ class ClockSampler:
     def summary(self):
         sm, mx, reasons = [], [], set()
         names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
-        for r in self.rows:
+        t_mark = getattr(self, "t_mark", 0.0)
+        for ts, r in self.rows:
+            if ts < t_mark:
+                continue
             try:
                 sm.append(float(r[0])); mx.append(float(r[1]))
             except (ValueError, IndexError):
@@ -190,7 +202,7 @@ class ScanSet:
         g = torch.Generator(device="cpu").manual_seed(seed)
         bf = torch.bfloat16
         B_, D_, L_, N_ = clips, D_INNER, SEQLEN, D_STATE
-        U = (L_ + _lib.VV_SCAN_UNIT - 1) // _lib.VV_SCAN_UNIT
+        U = (L_ + _lib.VV_SCAN_SEGMENT - 1) // _lib.VV_SCAN_SEGMENT
         r = lambda *s: torch.randn(*s, generator=g)  # noqa: E731
         self.host = dict(u=r(B_, D_, L_).to(bf), delta=(0.5 * r(B_, D_, L_)).to(bf), z=r(B_, D_, L_).to(bf),
                          B=r(B_, 1, N_, L_).to(bf), C=r(B_, 1, N_, L_).to(bf), dout=r(B_, D_, L_).to(bf))
@@ -298,10 +310,12 @@ def run_ours(args, rank, world, local_rank):
         torch.cuda.synchronize()
 
     step = lambda i: graphs[i % n_sets].replay()  # noqa: E731
-    for i in range(args.warmup):
-        step(i)
-    barrier()
     with ClockSampler(local_rank) as clk:
+        clk.wait_first_sample()
+        for i in range(args.warmup):
+            step(i)
+        barrier()
+        clk.mark()
         elapsed = time_events(lambda i: step(i + args.warmup), args.steps, torch)
         barrier()
     if world > 1:
@@ -470,8 +484,8 @@ def main():
         args.warmup = 1 if args.warmup is None else min(args.warmup, 3)
         run_reference(args, rank, world)
         return
-    args.steps = 200 if args.steps is None else args.steps
-    args.warmup = 20 if args.warmup is None else max(args.warmup, 3)
+    args.steps = 3000 if args.steps is None else args.steps
+    args.warmup = 100 if args.warmup is None else max(args.warmup, 3)
     run_ours(args, rank, world, local_rank)
 
 

@@ -41,14 +41,16 @@ enum {
     VV_ERR_ALIGN = -3         /* pointer not aligned to its element size */
 };
 
-/* Sequence positions one scan work unit covers.  Checkpoints and carries are per unit. */
+/* Sequence positions per checkpoint segment: scan states are checkpointed / carried every 64
+ * positions.  VV_SCAN_UNIT (4 segments) is the work unit of one warp in the backward main kernel. */
+#define VV_SCAN_SEGMENT 64
 #define VV_SCAN_UNIT 256
 
 int vv_version(void);
 const char *vv_last_error(void);
 
-/* number of scan units for a sequence of length L: ceil(L / VV_SCAN_UNIT) */
-int vv_scan_num_units(int seqlen);
+/* number of checkpoint segments for a sequence of length L: ceil(L / VV_SCAN_SEGMENT) */
+int vv_scan_num_segments(int seqlen);
 
 /* ------------------------------------------------------------------ causal depthwise conv1d
  * Replaces causal_conv1d_cuda.causal_conv1d_fwd / _bwd, channel-first layout only
@@ -80,11 +82,11 @@ int vv_conv1d_bwd(const vv_conv1d_args *a, void *stream);
  *   dt = softplus?(delta + delta_bias);  h_t = exp(dt A) h_{t-1} + dt B_t u_t;
  *   y_t = <C_t, h_t> + D u_t;  out = y;  out_z = y * silu(z).
  *
- * Workspaces (float32, caller-allocated, contents need not be initialised), U = vv_scan_num_units(L):
- *   agg  : 2 * B*D*U*N floats   per-unit scan aggregates (decay product, local state)
- *   chk  : B*D*U*N floats       fwd: state entering each unit (saved for bwd)
+ * Workspaces (float32, caller-allocated, contents need not be initialised), S = vv_scan_num_segments(L):
+ *   agg  : 2 * B*D*S*N floats   per-segment scan aggregates (decay product, local state)
+ *   chk  : B*D*S*N floats       fwd: state entering each segment (saved for bwd)
  *                               bwd: the same tensor, read
- *   radj : B*D*U*N floats       bwd only: adjoint state entering each unit from the right
+ *   radj : B*D*S*N floats       bwd only: adjoint state entering each segment from the right
  * The reference's `x` intermediate (B,D,n_chunks,2N) (selective_scan.cpp:307-313) is replaced by chk.
  */
 typedef struct {
@@ -123,7 +125,7 @@ int vv_scan_bwd(const vv_scan_args *a, void *stream);
 int vv_last_launch_count(void);
 
 /* Measurement aid (bench.py, ncu): restrict which of the three scan passes subsequent vv_scan_fwd /
- * vv_scan_bwd calls on this thread launch.  bit0: unit aggregates, bit1: carry fold, bit2: main
+ * vv_scan_bwd calls on this thread launch.  bit0: segment aggregates, bit1: carry fold, bit2: main
  * kernel.  Default 7 (all).  Returns the previous mask.  Workspaces must hold valid data from an
  * earlier full call when a pass is skipped. */
 int vv_scan_set_pass_mask(int mask);

@@ -47,8 +47,8 @@ def test_struct_layout_matches_c(tmp_path):
 
 def test_version_and_units(L):
     assert L.vv_version() == 100
-    assert L.vv_scan_num_units(20480) == 80
-    assert L.vv_scan_num_units(1) == 1 and L.vv_scan_num_units(257) == 2 and L.vv_scan_num_units(0) == 0
+    assert L.vv_scan_num_segments(20480) == 320
+    assert L.vv_scan_num_segments(1) == 1 and L.vv_scan_num_segments(65) == 2 and L.vv_scan_num_segments(0) == 0
 
 
 def test_bad_arguments_are_reported_not_launched(L):

@@ -10,7 +10,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "lib", "libvivim_b200.so")
 
 VV_F32, VV_F16, VV_BF16 = 0, 1, 2
-VV_SCAN_UNIT = 256
+VV_SCAN_SEGMENT = 64
 
 
 class ConvArgs(Structure):
@@ -50,7 +50,7 @@ class ScanArgs(Structure):
 
 
 # every symbol include/vivim_b200.h declares (checked by tests/test_cabi.py)
-EXPORTS = ("vv_version", "vv_last_error", "vv_scan_num_units", "vv_conv1d_fwd", "vv_conv1d_bwd",
+EXPORTS = ("vv_version", "vv_last_error", "vv_scan_num_segments", "vv_conv1d_fwd", "vv_conv1d_bwd",
            "vv_scan_fwd", "vv_scan_bwd", "vv_last_launch_count", "vv_scan_set_pass_mask")
 
 _lib = None
@@ -69,8 +69,8 @@ def lib() -> ctypes.CDLL:
         L.vv_last_launch_count.restype = c_int
         L.vv_scan_set_pass_mask.argtypes = [c_int]
         L.vv_scan_set_pass_mask.restype = c_int
-        L.vv_scan_num_units.argtypes = [c_int]
-        L.vv_scan_num_units.restype = c_int
+        L.vv_scan_num_segments.argtypes = [c_int]
+        L.vv_scan_num_segments.restype = c_int
         for name, argt in (("vv_conv1d_fwd", ConvArgs), ("vv_conv1d_bwd", ConvArgs),
                            ("vv_scan_fwd", ScanArgs), ("vv_scan_bwd", ScanArgs)):
             fn = getattr(L, name)

@@ -1,30 +1,24 @@
-// scan.cuh -- fused selective scan forward / backward for sm_100a.
+// scan.cuh -- backward main kernel of the fused selective scan for sm_100a.
 //
-// Replaces selective_scan_fwd_kernel / selective_scan_bwd_kernel of the reference
-// (mamba/csrc/selective_scan/selective_scan_fwd_kernel.cuh:67-303, selective_scan_bwd_kernel.cuh:75-489).
-// The algebra is the reference's: the associative operator (a0,b0)o(a1,b1) = (a1 a0, a1 b0 + b1)
-// (selective_scan_common.h:110-115), softplus with threshold 20, exp2f(dt * A * log2e).
+// Replaces selective_scan_bwd_kernel of the reference
+// (mamba/csrc/selective_scan/selective_scan_bwd_kernel.cuh:75-489).  The algebra is the reference's:
+// the associative operator (a0,b0)o(a1,b1) = (a1 a0, a1 b0 + b1) (selective_scan_common.h:110-115),
+// softplus with threshold 20, exp2f(dt * A * log2e), gradient formulas of :279-295 and :439-453.
 //
 // Design (B200-first, not a port).  The reference walks a whole (batch, channel) row inside one
-// CTA, chunk after chunk; at Vivim's shapes that is 128..1024 CTAs each serialising up to 20480
-// steps x 16 states.  Here the sequence is cut into UNITS of 256 positions and every
-// (batch, channel, unit) is an independent piece of work for one warp:
-//
-//   pass 1  scan_agg_kernel      per unit and state: the unit's aggregate (decay product, local state)
-//   pass 2  scan_carry_kernel    per (row, state): a serial fold over the units' aggregates
-//                                -> state entering each unit (forward: the checkpoint tensor `chk`,
-//                                   saved for the backward; reverse: the adjoint carry `radj`)
-//   pass 3  scan_fwd_main_kernel / scan_bwd_main_kernel   per unit, seeded by its carry
-//
-// so B*D*ceil(L/256) warps are in flight (10240 at the B=1 stage-1 shape) and no CTA waits on
-// another.  The backward recomputes the forward states of a unit from `chk` (checkpointed chunk
-// states, recomputed in the backward) and never reads a saved `out`.
+// CTA, chunk after chunk, last to first.  Here every (batch, channel, UNIT of 256 positions) is an
+// independent piece of work for one warp: the forward state entering the unit comes from the
+// checkpoint tensor `chk` written by the forward pass (checkpointed chunk states, recomputed in
+// the backward -- a saved `out` is never read), the adjoint entering it from the right comes from
+// `radj`, produced by the reverse segment-aggregate + carry passes of scan_seq.cuh.  So
+// B*D*ceil(L/256) warps are in flight (10240 at the B=1 stage-1 shape) and no CTA waits on another.
 //
 // Inside a warp: lane l owns positions [8l, 8l+8) of the unit (one 128-bit access per streamed
 // tensor, 512 contiguous bytes per warp request).  For one state n the lane runs the recurrence over
 // its 8 positions in registers (exp2 evaluated once per element and kept), the 32 lane aggregates
-// are combined by a 5-step warp-shuffle scan, and a second in-register sweep produces the states.
-// B and C rows of the unit are staged once per CTA in shared memory as fp32 (so the bf16->fp32
+// are combined by a 5-step warp-shuffle scan (once left-to-right for h, once right-to-left for the
+// adjoint), and a second in-register sweep produces states, adjoints and all gradient terms.
+// B and C rows of the unit are staged once per CTA in shared memory as fp32 (the bf16->fp32
 // conversion is paid once per CTA, not once per channel) in a slot order that makes each lane's two
 // 128-bit reads bank-conflict free, and are reused by every channel the CTA walks.
 // dB/dC are reduced over the channels of a CTA in shared memory (each warp owns a different state
@@ -35,6 +29,7 @@
 
 #include "../../include/vivim_b200.h"
 #include "common.cuh"
+#include "scan_seq.cuh"
 
 namespace vv {
 
@@ -125,187 +120,6 @@ __device__ __forceinline__ RowCoord row_coord(const vv_scan_args& a, int rows_se
     return c;
 }
 
-// ================================================================ pass 1: unit aggregates
-// kRev = false: (P, X) of h_t = a_t h_{t-1} + dt_t B_t u_t over the unit        (uses u, B)
-// kRev = true : (P, X) of r_t = a_{t+1} r_{t+1} + g_t C_t, g = dout*silu(z)    (uses dout, z, C)
-template <typename T, bool kVec, bool kRev>
-__global__ void __launch_bounds__(128) scan_agg_kernel(const vv_scan_args a, const int rows_seq) {
-    extern __shared__ float4 smem4[];
-    float4* tile = smem4;
-    const int L = a.seqlen, N = a.dstate;
-    {
-        const RowCoord c0 = row_coord(a, rows_seq, 0);
-        const T* m = kRev ? reinterpret_cast<const T*>(a.Cm) + c0.b * a.C_bs + c0.g * a.C_gs
-                          : reinterpret_cast<const T*>(a.Bm) + c0.b * a.B_bs + c0.g * a.B_gs;
-        fill_tile<T, kVec>(tile, m, kRev ? a.C_ns : a.B_ns, N, c0.unit, L);
-    }
-    __syncthreads();
-    const int U = gridDim.x;
-    for (int k = 0; k < rows_seq; ++k) {
-        const RowCoord c = row_coord(a, rows_seq, k);
-        const int lane = c.lane;
-        const int t0 = c.unit * kUnit + lane * kVecElems;
-        const float bias = a.delta_bias ? a.delta_bias[c.d] : 0.f;
-        float dt[8], coef[8];
-        load_dt<T, kVec>(reinterpret_cast<const T*>(a.delta) + c.b * a.delta_bs + c.d * a.delta_ds, t0, L, bias,
-                         a.delta_softplus != 0, dt);
-        float sum_dt = 0.f;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) sum_dt += dt[i];
-        if (!kRev) {
-            load8<T, kVec>(reinterpret_cast<const T*>(a.u) + c.b * a.u_bs + c.d * a.u_ds, t0, L, coef);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) coef[i] *= dt[i];
-        } else {
-            load8<T, kVec>(reinterpret_cast<const T*>(a.dout) + c.b * a.dout_bs + c.d * a.dout_ds, t0, L, coef);
-            if (a.z) {
-                float zv[8];
-                load8<T, kVec>(reinterpret_cast<const T*>(a.z) + c.b * a.z_bs + c.d * a.z_ds, t0, L, zv);
-#pragma unroll
-                for (int i = 0; i < 8; ++i) coef[i] *= zv[i] * sigmoid_f(zv[i]);
-            }
-            // the reverse recurrence multiplies by the decay of the NEXT position
-            float dt_next = __shfl_down_sync(0xffffffffu, dt[0], 1);
-            if (lane == 31) {
-                const int tn = t0 + kVecElems;
-                dt_next = 0.f;
-                if (tn < L) {
-                    float v = to_f32<T>(reinterpret_cast<const T*>(a.delta)[c.b * a.delta_bs + c.d * a.delta_ds + tn]) + bias;
-                    dt_next = a.delta_softplus ? softplus_f(v) : v;
-                }
-            }
-            sum_dt = sum_dt - dt[0] + dt_next;
-        }
-        const float A2_l = lane < N ? a.A[c.d * a.A_ds + lane * a.A_ns] * kLog2e : 0.f;
-        float myP = 1.f, myX = 0.f;
-        for (int n = 0; n < N; ++n) {
-            const float A2 = __shfl_sync(0xffffffffu, A2_l, n);
-            float m[8];
-            read_tile(tile, n, lane, m);
-            float X;
-            if (!kRev) {
-                X = 0.f;
-#pragma unroll
-                for (int i = 0; i < 8; ++i) X = fmaf(exp2f(dt[i] * A2), X, coef[i] * m[i]);
-            } else {
-                X = coef[7] * m[7];
-#pragma unroll
-                for (int i = 6; i >= 0; --i) X = fmaf(exp2f(dt[i + 1] * A2), X, coef[i] * m[i]);
-            }
-            float P = exp2f(A2 * sum_dt);
-            if (!kRev) warp_scan_fwd(P, X, lane); else warp_scan_rev(P, X, lane);
-            const float Pt = __shfl_sync(0xffffffffu, P, kRev ? 0 : 31);
-            const float Xt = __shfl_sync(0xffffffffu, X, kRev ? 0 : 31);
-            if (lane == n) { myP = Pt; myX = Xt; }
-        }
-        if (lane < N)
-            reinterpret_cast<float2*>(a.agg)[(c.row * U + c.unit) * N + lane] = make_float2(myP, myX);
-    }
-}
-
-// ================================================================ pass 2: fold unit aggregates
-// One thread per (row, state).  Forward: carry[u] = state entering unit u, last_state = state after
-// the last unit.  Reverse: carry[u] = adjoint entering unit u from the right.
-template <bool kRev>
-__global__ void __launch_bounds__(128) scan_carry_kernel(const float2* __restrict__ agg, float* __restrict__ carry,
-                                                         float* __restrict__ last_state, const int64_t rows,
-                                                         const int U, const int N) {
-    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= rows * N) return;
-    const int64_t row = idx / N;
-    const int n = (int)(idx - row * N);
-    const float2* __restrict__ ag = agg + row * U * N + n;
-    float* __restrict__ cr = carry + row * U * N + n;
-    float E = 0.f;
-    constexpr int kBatch = 8;  // independent loads in flight per thread
-    for (int u0 = 0; u0 < U; u0 += kBatch) {
-        float2 v[kBatch];
-#pragma unroll
-        for (int j = 0; j < kBatch; ++j) {
-            const int u = kRev ? U - 1 - (u0 + j) : u0 + j;
-            v[j] = (u0 + j < U) ? __ldg(ag + (int64_t)u * N) : make_float2(1.f, 0.f);
-        }
-#pragma unroll
-        for (int j = 0; j < kBatch; ++j) {
-            if (u0 + j < U) {
-                const int u = kRev ? U - 1 - (u0 + j) : u0 + j;
-                cr[(int64_t)u * N] = E;
-                E = fmaf(v[j].x, E, v[j].y);
-            }
-        }
-    }
-    if (!kRev && last_state) last_state[idx] = E;
-}
-
-// ================================================================ pass 3 (forward)
-template <typename T, bool kVec>
-__global__ void __launch_bounds__(128) scan_fwd_main_kernel(const vv_scan_args a, const int rows_seq) {
-    extern __shared__ float4 smem4[];
-    const int L = a.seqlen, N = a.dstate;
-    float4* tB = smem4;
-    float4* tC = smem4 + N * kSlots;
-    {
-        const RowCoord c0 = row_coord(a, rows_seq, 0);
-        fill_tile<T, kVec>(tB, reinterpret_cast<const T*>(a.Bm) + c0.b * a.B_bs + c0.g * a.B_gs, a.B_ns, N, c0.unit, L);
-        fill_tile<T, kVec>(tC, reinterpret_cast<const T*>(a.Cm) + c0.b * a.C_bs + c0.g * a.C_gs, a.C_ns, N, c0.unit, L);
-    }
-    __syncthreads();
-    const int U = gridDim.x;
-    for (int k = 0; k < rows_seq; ++k) {
-        const RowCoord c = row_coord(a, rows_seq, k);
-        const int lane = c.lane;
-        const int t0 = c.unit * kUnit + lane * kVecElems;
-        const float bias = a.delta_bias ? a.delta_bias[c.d] : 0.f;
-        const float Dv = a.D ? a.D[c.d] : 0.f;
-        float dt[8], du[8], y[8];
-        load_dt<T, kVec>(reinterpret_cast<const T*>(a.delta) + c.b * a.delta_bs + c.d * a.delta_ds, t0, L, bias,
-                         a.delta_softplus != 0, dt);
-        load8<T, kVec>(reinterpret_cast<const T*>(a.u) + c.b * a.u_bs + c.d * a.u_ds, t0, L, du);
-        float sum_dt = 0.f;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            y[i] = Dv * du[i];
-            du[i] *= dt[i];
-            sum_dt += dt[i];
-        }
-        const float A2_l = lane < N ? a.A[c.d * a.A_ds + lane * a.A_ns] * kLog2e : 0.f;
-        const float E_l = lane < N ? a.chk[(c.row * U + c.unit) * N + lane] : 0.f;
-        for (int n = 0; n < N; ++n) {
-            const float A2 = __shfl_sync(0xffffffffu, A2_l, n);
-            const float E = __shfl_sync(0xffffffffu, E_l, n);
-            float bm[8], cm[8], dec[8];
-            read_tile(tB, n, lane, bm);
-            read_tile(tC, n, lane, cm);
-            float X = 0.f;
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                dec[i] = exp2f(dt[i] * A2);
-                bm[i] *= du[i];
-                X = fmaf(dec[i], X, bm[i]);
-            }
-            float P = exp2f(A2 * sum_dt);
-            warp_scan_fwd(P, X, lane);
-            float Pex = __shfl_up_sync(0xffffffffu, P, 1);
-            float Xex = __shfl_up_sync(0xffffffffu, X, 1);
-            if (lane == 0) { Pex = 1.f; Xex = 0.f; }
-            float h = fmaf(Pex, E, Xex);  // state entering this lane's first position
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                h = fmaf(dec[i], h, bm[i]);
-                y[i] = fmaf(cm[i], h, y[i]);
-            }
-        }
-        if (a.out) store8<T, kVec>(reinterpret_cast<T*>(a.out) + c.b * a.out_bs + c.d * a.out_ds, t0, L, y);
-        if (a.z) {
-            float zv[8];
-            load8<T, kVec>(reinterpret_cast<const T*>(a.z) + c.b * a.z_bs + c.d * a.z_ds, t0, L, zv);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) y[i] *= zv[i] * sigmoid_f(zv[i]);
-            store8<T, kVec>(reinterpret_cast<T*>(a.out_z) + c.b * a.outz_bs + c.d * a.outz_ds, t0, L, y);
-        }
-    }
-}
-
 // ================================================================ pass 3 (backward)
 // Gradient formulas (real A, variable B and C): selective_scan_bwd_kernel.cuh:279-295, 439-453.
 template <typename T, bool kVec>
@@ -318,7 +132,7 @@ __global__ void __launch_bounds__(128) scan_bwd_main_kernel(const vv_scan_args a
     float4* tdB = tC + N * kSlots;
     float4* tdC = tdB + N * kSlots;
     float* s_dA = reinterpret_cast<float*>(tdC + N * kSlots);  // [W][N][kDaPitch]
-    const int U = gridDim.x;
+    const int S = (L + kSeg - 1) / kSeg;   // chk / radj are indexed by 64-position segments
     {
         const RowCoord c0 = row_coord(a, rows_seq, 0);
         fill_tile<T, kVec>(tB, reinterpret_cast<const T*>(a.Bm) + c0.b * a.B_bs + c0.g * a.B_gs, a.B_ns, N, c0.unit, L);
@@ -367,8 +181,11 @@ __global__ void __launch_bounds__(128) scan_bwd_main_kernel(const vv_scan_args a
         }
         const float sum_dt_rev = sum_dt - dt[0] + dt_next;
         const float A_l = lane < N ? a.A[c.d * a.A_ds + lane * a.A_ns] : 0.f;
-        const float E_l = lane < N ? a.chk[(c.row * U + c.unit) * N + lane] : 0.f;
-        const float R_l = lane < N ? a.radj[(c.row * U + c.unit) * N + lane] : 0.f;
+        // state entering the unit's first segment; adjoint entering its last segment from the right
+        const int seg_first = c.unit * kSegPerUnit;
+        const int seg_last = min(seg_first + kSegPerUnit - 1, S - 1);
+        const float E_l = lane < N ? a.chk[(c.row * S + seg_first) * N + lane] : 0.f;
+        const float R_l = lane < N ? a.radj[(c.row * S + seg_last) * N + lane] : 0.f;
         float* my_dA = s_dA + c.warp * N * kDaPitch;
 
         for (int j = 0; j < N; ++j) {

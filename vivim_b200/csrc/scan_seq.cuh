@@ -1,0 +1,522 @@
+// scan_seq.cuh -- channel-per-lane, time-sequential selective-scan kernels for sm_100a.
+//
+// Used for everything that only needs the recurrence in ONE direction: the segment aggregates
+// (forward and reverse), and the whole forward pass.  Layout:
+//
+//   * the sequence is cut into SEGMENTS of 64 positions; a CTA (4 warps) owns 32 channels x one
+//     segment.  Four adjacent lanes share a channel and split its N states (N/4 each, in registers);
+//     every lane walks the 64 positions in order, so a state recurrence is one FMA chain and there
+//     is no cross-lane scan and no block barrier on the data path:
+//         per (channel, position, state): 1 FMUL (dt*A), 1 MUFU.EX2, 1 FMUL (drive*B), 1 FFMA (h),
+//         1 FFMA (y += C h)  +  1/4 LDS.128 each for B and C,
+//     plus a 2-step shuffle reduce-scatter of the y partial sums per 8 positions.  That is ~half the
+//     instructions of a warp-scan formulation.  Splitting the states over lanes (instead of one
+//     lane per channel) quadruples the warps in flight -- 5120 at the B=1 stage-1 shape -- which is
+//     what keeps the MUFU pipe fed; the kernel is bound by the MUFU.EX2 rate (16 lanes/clk/SM),
+//     not by HBM: see DESIGN.md section 5.
+//   * softplus(delta + bias) and the drive dt*u (or the gated upstream gradient) are evaluated once
+//     per (channel, position) by a pre-pass into fp32 shared tiles, not once per lane.
+//   * streamed rows (u, delta, z, dout) of the CTA's channels are staged through shared memory as
+//     [channel][64] tiles in their I/O dtype: the global side is 128-bit coalesced (a warp request
+//     covers 4 rows x 128 B), the shared side is read back transposed (lane = channel) with a
+//     16-byte row pad that makes the 128-bit reads bank-conflict free.  The gated output is written
+//     over the u tile (each thread owns its row) and leaves with the same coalesced pattern.
+//   * B / C of the segment are staged once per CTA as fp32 [position][state], so every lane reads the
+//     same address (broadcast) and the bf16->fp32 conversion is paid once per CTA.
+//
+//   pass 1  seg_agg_kernel    (P, X) of every (row, segment, state), forward or reverse
+//   pass 2  seg_carry_kernel  per row: fold the segment aggregates -> state entering each segment
+//                             (forward: chk, saved for the backward; reverse: radj)
+//   pass 3  seg_fwd_kernel    forward outputs, seeded by chk
+#pragma once
+
+#include "../../include/vivim_b200.h"
+#include "common.cuh"
+
+namespace vv {
+
+constexpr int kSeg = 64;                      // positions per segment
+constexpr int kSegThreads = 128;              // 4 warps per CTA
+constexpr int kSegRows = 32;                  // channels per CTA: 4 lanes per channel
+constexpr int kSegPerUnit = VV_SCAN_UNIT / kSeg;
+
+template <typename T> struct SegTile {
+    static constexpr int kPitch = kSeg * (int)sizeof(T) + 16;   // bytes per channel row (odd multiple of 16)
+};
+
+// ---------------------------------------------------------------- tile staging
+// Asynchronous 16-byte global->shared copies (LDGSTS): a thread issues all of its copies back to
+// back without holding registers, so the DRAM latency of a tile fill is paid once, not once per
+// load->store round trip.  src_bytes == 0 zero-fills the destination (positions outside [0, L)).
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc, int src_bytes) {
+    const unsigned dst = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(dst), "l"(gsrc), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+    asm volatile("cp.async.commit_group;\n" ::: "memory");
+    asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+}
+
+// rows [0, nrows) of `base` (row stride ds), positions [t0, t0 + 64) -> tile[row][..] in dtype T.
+// kVec: asynchronous (finish with cp_async_wait_all + __syncthreads); else synchronous scalar loads.
+template <typename T, bool kVec>
+__device__ __forceinline__ void stage_rows_in(unsigned char* __restrict__ tile, const T* __restrict__ base, int64_t ds,
+                                              int nrows, int t0, int L) {
+    constexpr int kChunks = kSeg / 8;   // 8-element chunks per row
+    for (int idx = threadIdx.x; idx < kSegRows * kChunks; idx += blockDim.x) {
+        const int r = idx / kChunks, c = idx - r * kChunks;
+        T* dst = reinterpret_cast<T*>(tile + r * SegTile<T>::kPitch) + c * 8;
+        const int t = t0 + c * 8;
+        if (kVec) {
+            const bool ok = r < nrows && t < L;
+            const T* src = ok ? base + r * ds + t : base;
+            cp_async16(dst, src, ok ? 16 : 0);
+            if (sizeof(T) == 4) cp_async16(reinterpret_cast<unsigned char*>(dst) + 16,
+                                           reinterpret_cast<const unsigned char*>(src) + (ok ? 16 : 0), ok ? 16 : 0);
+        } else {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) dst[i] = (r < nrows && t + i < L) ? base[r * ds + t + i] : from_f32<T>(0.f);
+        }
+    }
+}
+
+template <typename T, bool kVec>
+__device__ __forceinline__ void stage_rows_out(const unsigned char* __restrict__ tile, T* __restrict__ base, int64_t ds,
+                                               int nrows, int t0, int L) {
+    constexpr int kChunks = kSeg / 8;
+    for (int idx = threadIdx.x; idx < kSegRows * kChunks; idx += blockDim.x) {
+        const int r = idx / kChunks, c = idx - r * kChunks;
+        const T* src = reinterpret_cast<const T*>(tile + r * SegTile<T>::kPitch) + c * 8;
+        const int t = t0 + c * 8;
+        if (r >= nrows) continue;
+        if (kVec) {
+            if (t < L) {
+                uint4* dst = reinterpret_cast<uint4*>(base + r * ds + t);
+                dst[0] = reinterpret_cast<const uint4*>(src)[0];
+                if (sizeof(T) == 4) dst[1] = reinterpret_cast<const uint4*>(src)[1];
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+                if (t + i < L) base[r * ds + t + i] = src[i];
+        }
+    }
+}
+
+// 8 consecutive positions of this thread's own row of a staged tile -> fp32
+template <typename T>
+__device__ __forceinline__ void tile_read8(const unsigned char* __restrict__ row, int c, float (&v)[8]) {
+    load8_plain<T>(reinterpret_cast<const T*>(row) + c * 8, v);
+}
+template <typename T>
+__device__ __forceinline__ void tile_write8(unsigned char* __restrict__ row, int c, const float (&v)[8]) {
+    store8_vec<T>(reinterpret_cast<T*>(row) + c * 8, v);
+}
+
+// B or C of the segment.  Step 1 (asynchronous when kVec): raw rows -> stage[n][64] in dtype T.
+template <typename T, bool kVec, int NB>
+__device__ __forceinline__ void stage_state_raw(T* __restrict__ stage, const T* __restrict__ base, int64_t ns,
+                                                int N, int t0, int L) {
+    constexpr int kChunks = kSeg / 8;
+    for (int idx = threadIdx.x; idx < NB * kChunks; idx += blockDim.x) {
+        const int n = idx / kChunks, c = idx - n * kChunks;
+        T* dst = stage + n * kSeg + c * 8;
+        const int t = t0 + c * 8;
+        if (kVec) {
+            const bool ok = n < N && t < L;
+            const T* src = ok ? base + n * ns + t : base;
+            cp_async16(dst, src, ok ? 16 : 0);
+            if (sizeof(T) == 4) cp_async16(reinterpret_cast<unsigned char*>(dst) + 16,
+                                           reinterpret_cast<const unsigned char*>(src) + (ok ? 16 : 0), ok ? 16 : 0);
+        } else {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) dst[i] = (n < N && t + i < L) ? base[n * ns + t + i] : from_f32<T>(0.f);
+        }
+    }
+}
+// Step 2 (after the copies landed and a barrier): stage[n][64] -> fp32 tile[position][NB].  Every lane
+// of the compute phase reads the same tile address (broadcast), and the 16-bit -> fp32 conversion
+// is paid once per CTA.
+template <typename T, int NB>
+__device__ __forceinline__ void transpose_state_tile(float* __restrict__ tile, const T* __restrict__ stage) {
+    constexpr int kChunks = kSeg / 8;
+    for (int idx = threadIdx.x; idx < NB * kChunks; idx += blockDim.x) {
+        const int c = idx / NB, n = idx - c * NB;   // n fastest: shared stores spread over banks
+        float v[8];
+        load8_plain<T>(stage + n * kSeg + c * 8, v);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) tile[(c * 8 + i) * NB + n] = v[i];
+    }
+}
+
+template <typename T> struct SegSmem {
+    static constexpr int kRawTile = kSegRows * SegTile<T>::kPitch;       // [32][64] in dtype T
+    static constexpr int kF32Pitch = kSeg * 4 + 16;                        // bytes per row of an fp32 tile
+    static constexpr int kF32Tile = kSegRows * kF32Pitch;                  // [32][64] fp32
+};
+
+struct SegCoord {
+    int b, g, d0, nrows, seg, t0;   // d0: first channel of the CTA, nrows: valid channels in the CTA
+};
+
+__device__ __forceinline__ SegCoord seg_coord(const vv_scan_args& a) {
+    SegCoord c;
+    const int dpg = a.dim / a.ngroups;
+    const int blocks_per_group = (dpg + kSegRows - 1) / kSegRows;
+    c.seg = blockIdx.x;
+    c.t0 = c.seg * kSeg;
+    c.b = blockIdx.z;
+    c.g = blockIdx.y / blocks_per_group;
+    const int off = (blockIdx.y - c.g * blocks_per_group) * kSegRows;
+    c.d0 = c.g * dpg + off;
+    c.nrows = min(kSegRows, dpg - off);
+    return c;
+}
+
+// NQ consecutive fp32 states of one position (16-byte aligned when NQ % 4 == 0, 8-byte when NQ == 2)
+template <int NQ>
+__device__ __forceinline__ void load_states(const float* __restrict__ p, float (&v)[NQ]) {
+    if (NQ % 4 == 0) {
+#pragma unroll
+        for (int k = 0; k < NQ / 4; ++k) {
+            const float4 x = reinterpret_cast<const float4*>(p)[k];
+            v[4 * k] = x.x; v[4 * k + 1] = x.y; v[4 * k + 2] = x.z; v[4 * k + 3] = x.w;
+        }
+    } else {
+        const float2 x = *reinterpret_cast<const float2*>(p);
+        v[0] = x.x; v[1] = x.y;
+    }
+}
+
+// Pre-pass of one lane: for chunks {q, q + 4} of its channel row, dt = softplus?(raw + bias) (0 outside
+// [0, L)) and coef -> fp32 tiles.  kind 0: coef = dt * u (forward drive); kind 1: coef = dout * silu(z).
+template <typename T, int kKind>
+__device__ __forceinline__ void seg_prepass(const unsigned char* __restrict__ raw_dt, const unsigned char* __restrict__ raw_cf,
+                                            const unsigned char* __restrict__ raw_z, bool has_z,
+                                            unsigned char* __restrict__ f_dt, unsigned char* __restrict__ f_cf,
+                                            int q, int t0, int L, float bias, bool sp) {
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+        const int ch = q + 4 * k;
+        float dt[8], cf[8];
+        tile_read8<T>(raw_dt, ch, dt);
+        tile_read8<T>(raw_cf, ch, cf);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            float v = dt[i] + bias;
+            if (sp) v = softplus_f(v);
+            dt[i] = (t0 + ch * 8 + i < L) ? v : 0.f;
+        }
+        if (kKind == 0) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) cf[i] *= dt[i];
+        } else if (has_z) {
+            float zv[8];
+            tile_read8<T>(raw_z, ch, zv);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) cf[i] *= zv[i] * sigmoid_f(zv[i]);
+        }
+        store8_vec<float>(reinterpret_cast<float*>(f_dt) + ch * 8, dt);
+        store8_vec<float>(reinterpret_cast<float*>(f_cf) + ch * 8, cf);
+    }
+}
+
+// ================================================================ pass 1: segment aggregates
+// Lane (channel r, quad q) owns states [q*NQ, (q+1)*NQ) of channel r, NQ = NB/4.
+// smem: [raw delta][raw coef][raw z (rev)][f32 dt][f32 coef][state tile fp32][raw state stage]
+// kRev = false: (P, X) of h_t = a_t h_{t-1} + dt_t B_t u_t over the segment      (uses u, B)
+// kRev = true : (P, X) of r_t = a_{t+1} r_{t+1} + g_t C_t, g = dout*silu(z)     (uses dout, z, C)
+template <typename T, bool kVec, int NB, bool kRev>
+__global__ void __launch_bounds__(kSegThreads) seg_agg_kernel(const vv_scan_args a) {
+    constexpr int NQ = NB / 4;
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int L = a.seqlen, N = a.dstate;
+    const SegCoord c = seg_coord(a);
+    unsigned char* t_dt = smem;
+    unsigned char* t_cf = t_dt + SegSmem<T>::kRawTile;
+    unsigned char* t_z = t_cf + SegSmem<T>::kRawTile;
+    unsigned char* f_dt = t_z + (kRev ? SegSmem<T>::kRawTile : 0);
+    unsigned char* f_cf = f_dt + SegSmem<T>::kF32Tile;
+    float* t_m = reinterpret_cast<float*>(f_cf + SegSmem<T>::kF32Tile);
+    T* t_raw = reinterpret_cast<T*>(t_m + kSeg * NB);
+
+    stage_rows_in<T, kVec>(t_dt, reinterpret_cast<const T*>(a.delta) + c.b * a.delta_bs + c.d0 * a.delta_ds, a.delta_ds,
+                           c.nrows, c.t0, L);
+    if (!kRev) {
+        stage_rows_in<T, kVec>(t_cf, reinterpret_cast<const T*>(a.u) + c.b * a.u_bs + c.d0 * a.u_ds, a.u_ds, c.nrows, c.t0, L);
+        stage_state_raw<T, kVec, NB>(t_raw, reinterpret_cast<const T*>(a.Bm) + c.b * a.B_bs + c.g * a.B_gs, a.B_ns, N, c.t0, L);
+    } else {
+        stage_rows_in<T, kVec>(t_cf, reinterpret_cast<const T*>(a.dout) + c.b * a.dout_bs + c.d0 * a.dout_ds, a.dout_ds,
+                               c.nrows, c.t0, L);
+        if (a.z)
+            stage_rows_in<T, kVec>(t_z, reinterpret_cast<const T*>(a.z) + c.b * a.z_bs + c.d0 * a.z_ds, a.z_ds, c.nrows, c.t0, L);
+        stage_state_raw<T, kVec, NB>(t_raw, reinterpret_cast<const T*>(a.Cm) + c.b * a.C_bs + c.g * a.C_gs, a.C_ns, N, c.t0, L);
+    }
+    // per-lane constants are fetched while the copies are in flight
+    const int r = threadIdx.x >> 2, q = threadIdx.x & 3;
+    const bool live = r < c.nrows;
+    const int d = c.d0 + (live ? r : 0);
+    const float bias = a.delta_bias ? a.delta_bias[d] : 0.f;
+    const bool sp = a.delta_softplus != 0;
+    float A2[NQ], h[NQ], dec[NQ];
+#pragma unroll
+    for (int k = 0; k < NQ; ++k) {
+        const int n = q * NQ + k;
+        A2[k] = n < N ? a.A[d * a.A_ds + n * a.A_ns] * kLog2e : 0.f;
+        h[k] = 0.f;
+        dec[k] = 1.f;
+    }
+    float sum_dt = 0.f;
+    if (kRev) {
+        // decay of the first position of the NEXT segment multiplies this segment's last position
+        const int tn = c.t0 + kSeg;
+        float dt_next = 0.f;
+        if (tn < L) {
+            const float v = to_f32<T>(reinterpret_cast<const T*>(a.delta)[c.b * a.delta_bs + d * a.delta_ds + tn]) + bias;
+            dt_next = sp ? softplus_f(v) : v;
+        }
+        sum_dt = dt_next;
+#pragma unroll
+        for (int k = 0; k < NQ; ++k) dec[k] = exp2f(dt_next * A2[k]);
+    }
+    if (kVec) cp_async_wait_all();
+    __syncthreads();
+    transpose_state_tile<T, NB>(t_m, t_raw);
+    seg_prepass<T, kRev ? 1 : 0>(t_dt + r * SegTile<T>::kPitch, t_cf + r * SegTile<T>::kPitch, t_z + r * SegTile<T>::kPitch,
+                                 a.z != nullptr, f_dt + r * SegSmem<T>::kF32Pitch, f_cf + r * SegSmem<T>::kF32Pitch,
+                                 q, c.t0, L, bias, sp);
+    __syncthreads();
+    if (!live) return;
+    const float4* my_dt = reinterpret_cast<const float4*>(f_dt + r * SegSmem<T>::kF32Pitch);
+    const float4* my_cf = reinterpret_cast<const float4*>(f_cf + r * SegSmem<T>::kF32Pitch);
+    float dt_first = 0.f;
+#pragma unroll 2
+    for (int jb = 0; jb < kSeg / 4; ++jb) {
+        const int j = kRev ? kSeg / 4 - 1 - jb : jb;
+        const float4 d4 = my_dt[j], c4 = my_cf[j];
+        const float dts[4] = {d4.x, d4.y, d4.z, d4.w};
+        const float cfs[4] = {c4.x, c4.y, c4.z, c4.w};
+#pragma unroll
+        for (int ii = 0; ii < 4; ++ii) {
+            const int i = kRev ? 3 - ii : ii;
+            const float dti = dts[i];
+            sum_dt += dti;
+            float m[NQ];
+            load_states<NQ>(t_m + (j * 4 + i) * NB + q * NQ, m);
+            if (!kRev) {
+#pragma unroll
+                for (int k = 0; k < NQ; ++k) h[k] = fmaf(exp2f(dti * A2[k]), h[k], cfs[i] * m[k]);
+            } else {
+                // r_t = a_{t+1} r_{t+1} + g_t C_t ; then remember a_t for the next (earlier) position
+#pragma unroll
+                for (int k = 0; k < NQ; ++k) h[k] = fmaf(dec[k], h[k], cfs[i] * m[k]);
+#pragma unroll
+                for (int k = 0; k < NQ; ++k) dec[k] = exp2f(dti * A2[k]);
+            }
+        }
+        if (kRev && j == 0) dt_first = dts[0];
+    }
+    if (kRev) sum_dt -= dt_first;   // product of a_{t+1} over the segment
+    const int S = gridDim.x;
+    float2* out = reinterpret_cast<float2*>(a.agg) + (((int64_t)c.b * a.dim + d) * S + c.seg) * N;
+#pragma unroll
+    for (int k = 0; k < NQ; ++k) {
+        const int n = q * NQ + k;
+        if (n < N) out[n] = make_float2(exp2f(A2[k] * sum_dt), h[k]);
+    }
+}
+
+// ================================================================ pass 2: fold segment aggregates
+// One CTA of 512 threads per row.  Thread (k, n): chunk k of the row's segments (in scan order),
+// state n.  Each thread folds its few segments, the chunk aggregates are combined through shared
+// memory, and a second sweep writes the state entering every segment.  Forward: carry[s] = state
+// entering segment s (chk), last_state = state after the last one; reverse: carry[s] = adjoint
+// entering segment s from the right (radj).  All loads of a thread are independent of its FMA chain.
+constexpr int kCarryThreads = 512;
+constexpr int kCarryMaxPer = 16;   // segments a thread keeps in registers between the two sweeps
+
+template <bool kRev>
+__global__ void __launch_bounds__(kCarryThreads) seg_carry_kernel(const float2* __restrict__ agg, float* __restrict__ carry,
+                                                                  float* __restrict__ last_state, const int S, const int N) {
+    __shared__ float2 s_chunk[kCarryThreads];
+    const int64_t row = blockIdx.x;
+    const int chunks = kCarryThreads / N;
+    const int k = threadIdx.x / N, n = threadIdx.x - k * N;
+    const int per = (S + chunks - 1) / chunks;
+    const int lo = min(k * per, S), hi = min(lo + per, S);   // this thread's segments, in scan order
+    const float2* __restrict__ ag = agg + row * S * N + n;
+    float* __restrict__ cr = carry + row * S * N + n;
+    const bool active = k < chunks;
+    const bool cached = per <= kCarryMaxPer;
+    float2 v[kCarryMaxPer];
+    float P = 1.f, X = 0.f;
+    if (active) {
+        if (cached) {
+#pragma unroll
+            for (int j = 0; j < kCarryMaxPer; ++j) {
+                const int q = lo + j;
+                v[j] = q < hi ? __ldg(ag + (int64_t)(kRev ? S - 1 - q : q) * N) : make_float2(1.f, 0.f);
+            }
+#pragma unroll
+            for (int j = 0; j < kCarryMaxPer; ++j) {
+                X = fmaf(v[j].x, X, v[j].y);
+                P *= v[j].x;
+            }
+        } else {
+#pragma unroll 4
+            for (int q = lo; q < hi; ++q) {
+                const float2 w = __ldg(ag + (int64_t)(kRev ? S - 1 - q : q) * N);
+                X = fmaf(w.x, X, w.y);
+                P *= w.x;
+            }
+        }
+        s_chunk[threadIdx.x] = make_float2(P, X);
+    }
+    __syncthreads();
+    if (!active) return;
+    float E = 0.f;
+    for (int kk = 0; kk < k; ++kk) {
+        const float2 w = s_chunk[kk * N + n];
+        E = fmaf(w.x, E, w.y);
+    }
+    if (cached) {
+#pragma unroll
+        for (int j = 0; j < kCarryMaxPer; ++j) {
+            const int q = lo + j;
+            if (q < hi) cr[(int64_t)(kRev ? S - 1 - q : q) * N] = E;
+            E = fmaf(v[j].x, E, v[j].y);
+        }
+    } else {
+#pragma unroll 4
+        for (int q = lo; q < hi; ++q) {
+            const int s = kRev ? S - 1 - q : q;
+            const float2 w = __ldg(ag + (int64_t)s * N);
+            cr[(int64_t)s * N] = E;
+            E = fmaf(w.x, E, w.y);
+        }
+    }
+    if (!kRev && last_state && hi == S && lo < S) last_state[row * N + n] = E;
+}
+
+// ================================================================ pass 3: forward outputs
+// smem: [raw delta -> pre-gate y][raw u -> gated y][raw z][f32 dt][f32 drive][B tile][C tile][raw B][raw C]
+template <typename T, bool kVec, int NB>
+__global__ void __launch_bounds__(kSegThreads) seg_fwd_kernel(const vv_scan_args a) {
+    constexpr int NQ = NB / 4;
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int L = a.seqlen, N = a.dstate;
+    const SegCoord c = seg_coord(a);
+    unsigned char* t_dt = smem;
+    unsigned char* t_u = t_dt + SegSmem<T>::kRawTile;
+    unsigned char* t_z = t_u + SegSmem<T>::kRawTile;
+    unsigned char* f_dt = t_z + SegSmem<T>::kRawTile;
+    unsigned char* f_dr = f_dt + SegSmem<T>::kF32Tile;
+    float* t_B = reinterpret_cast<float*>(f_dr + SegSmem<T>::kF32Tile);
+    float* t_C = t_B + kSeg * NB;
+    T* raw_B = reinterpret_cast<T*>(t_C + kSeg * NB);
+    T* raw_C = raw_B + kSeg * NB;
+
+    stage_rows_in<T, kVec>(t_dt, reinterpret_cast<const T*>(a.delta) + c.b * a.delta_bs + c.d0 * a.delta_ds, a.delta_ds,
+                           c.nrows, c.t0, L);
+    stage_rows_in<T, kVec>(t_u, reinterpret_cast<const T*>(a.u) + c.b * a.u_bs + c.d0 * a.u_ds, a.u_ds, c.nrows, c.t0, L);
+    if (a.z)
+        stage_rows_in<T, kVec>(t_z, reinterpret_cast<const T*>(a.z) + c.b * a.z_bs + c.d0 * a.z_ds, a.z_ds, c.nrows, c.t0, L);
+    stage_state_raw<T, kVec, NB>(raw_B, reinterpret_cast<const T*>(a.Bm) + c.b * a.B_bs + c.g * a.B_gs, a.B_ns, N, c.t0, L);
+    stage_state_raw<T, kVec, NB>(raw_C, reinterpret_cast<const T*>(a.Cm) + c.b * a.C_bs + c.g * a.C_gs, a.C_ns, N, c.t0, L);
+
+    const int r = threadIdx.x >> 2, q = threadIdx.x & 3;
+    const bool live = r < c.nrows;
+    const int d = c.d0 + (live ? r : 0);
+    const float bias = a.delta_bias ? a.delta_bias[d] : 0.f;
+    const float Dv = a.D ? a.D[d] : 0.f;
+    const bool sp = a.delta_softplus != 0;
+    const int S = gridDim.x;
+    float A2[NQ], h[NQ];
+    {
+        const float* E = a.chk + (((int64_t)c.b * a.dim + d) * S + c.seg) * N;
+#pragma unroll
+        for (int k = 0; k < NQ; ++k) {
+            const int n = q * NQ + k;
+            A2[k] = n < N ? a.A[d * a.A_ds + n * a.A_ns] * kLog2e : 0.f;
+            h[k] = n < N ? E[n] : 0.f;
+        }
+    }
+    if (kVec) cp_async_wait_all();
+    __syncthreads();
+    transpose_state_tile<T, NB>(t_B, raw_B);
+    transpose_state_tile<T, NB>(t_C, raw_C);
+    seg_prepass<T, 0>(t_dt + r * SegTile<T>::kPitch, t_u + r * SegTile<T>::kPitch, nullptr, false,
+                      f_dt + r * SegSmem<T>::kF32Pitch, f_dr + r * SegSmem<T>::kF32Pitch, q, c.t0, L, bias, sp);
+    __syncthreads();
+    {
+        // The raw delta / u rows are consumed; they now receive the pre-gate and the gated output.
+        T* o_pre = reinterpret_cast<T*>(t_dt + r * SegTile<T>::kPitch);
+        T* o_gate = reinterpret_cast<T*>(t_u + r * SegTile<T>::kPitch);
+        const T* my_u = reinterpret_cast<const T*>(t_u + r * SegTile<T>::kPitch);
+        const T* my_z = reinterpret_cast<const T*>(t_z + r * SegTile<T>::kPitch);
+        const float4* my_dt = reinterpret_cast<const float4*>(f_dt + r * SegSmem<T>::kF32Pitch);
+        const float4* my_dr = reinterpret_cast<const float4*>(f_dr + r * SegSmem<T>::kF32Pitch);
+        const bool b1 = (q & 2) != 0, b0 = (q & 1) != 0;
+#pragma unroll 1
+        for (int ch = 0; ch < kSeg / 8; ++ch) {
+            // this lane finalises positions {2q, 2q+1} of the chunk: D*u skip and gate, independent of the recurrences
+            const int p0 = ch * 8 + 2 * q;
+            const float u0 = to_f32<T>(my_u[p0]), u1 = to_f32<T>(my_u[p0 + 1]);
+            float g0 = 1.f, g1 = 1.f;
+            if (a.z) {
+                g0 = to_f32<T>(my_z[p0]);
+                g1 = to_f32<T>(my_z[p0 + 1]);
+                g0 *= sigmoid_f(g0);
+                g1 *= sigmoid_f(g1);
+            }
+            float y[8];
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+                const float4 d4 = my_dt[ch * 2 + half], r4 = my_dr[ch * 2 + half];
+                const float dts[4] = {d4.x, d4.y, d4.z, d4.w};
+                const float drs[4] = {r4.x, r4.y, r4.z, r4.w};
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int t = ch * 8 + half * 4 + i;
+                    float bm[NQ], cm[NQ];
+                    load_states<NQ>(t_B + t * NB + q * NQ, bm);
+                    load_states<NQ>(t_C + t * NB + q * NQ, cm);
+                    float acc = 0.f;
+#pragma unroll
+                    for (int k = 0; k < NQ; ++k) {
+                        h[k] = fmaf(exp2f(dts[i] * A2[k]), h[k], drs[i] * bm[k]);
+                        acc = fmaf(cm[k], h[k], acc);
+                    }
+                    y[half * 4 + i] = acc;
+                }
+            }
+            // reduce-scatter of the 8 partial sums over the 4 lanes of the channel: lane q ends with {2q, 2q+1}
+            float keep[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float send = b1 ? y[j] : y[4 + j];
+                const float recv = __shfl_xor_sync(0xffffffffu, send, 2);
+                keep[j] = (b1 ? y[4 + j] : y[j]) + recv;
+            }
+            float fin[2];
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                const float send = b0 ? keep[j] : keep[2 + j];
+                const float recv = __shfl_xor_sync(0xffffffffu, send, 1);
+                fin[j] = (b0 ? keep[2 + j] : keep[j]) + recv;
+            }
+            fin[0] = fmaf(Dv, u0, fin[0]);
+            fin[1] = fmaf(Dv, u1, fin[1]);
+            __syncwarp();   // all four lanes have read their u / z of this chunk before it is overwritten
+            if (a.out) { o_pre[p0] = from_f32<T>(fin[0]); o_pre[p0 + 1] = from_f32<T>(fin[1]); }
+            if (a.z) { o_gate[p0] = from_f32<T>(fin[0] * g0); o_gate[p0 + 1] = from_f32<T>(fin[1] * g1); }
+        }
+    }
+    __syncthreads();
+    if (a.out)
+        stage_rows_out<T, kVec>(t_dt, reinterpret_cast<T*>(a.out) + c.b * a.out_bs + c.d0 * a.out_ds, a.out_ds, c.nrows, c.t0, L);
+    if (a.z)
+        stage_rows_out<T, kVec>(t_u, reinterpret_cast<T*>(a.out_z) + c.b * a.outz_bs + c.d0 * a.outz_ds, a.outz_ds, c.nrows, c.t0, L);
+}
+
+}  // namespace vv

@@ -9,6 +9,7 @@
 #include "../../include/vivim_b200.h"
 #include "conv1d.cuh"
 #include "scan.cuh"
+#include "scan_seq.cuh"
 
 namespace {
 
@@ -100,7 +101,7 @@ struct ScanPlan {
 
 ScanPlan plan_scan(const vv_scan_args& a) {
     ScanPlan p;
-    p.units = vv_scan_num_units(a.seqlen);
+    p.units = (a.seqlen + VV_SCAN_UNIT - 1) / VV_SCAN_UNIT;
     const int dpg = a.dim / a.ngroups;
     p.W = 1;
     for (int w : {4, 2}) {
@@ -171,51 +172,91 @@ int set_smem(K kernel, size_t bytes) {
     return VV_OK;
 }
 
+// geometry of the segment kernels (scan_seq.cuh): 32 channels x one 64-position segment per CTA
+struct SegPlan {
+    int NB;        // compile-time state block: 8, 16 or 32
+    int segs;
+    dim3 grid;
+};
+
+SegPlan plan_seg(const vv_scan_args& a) {
+    SegPlan p;
+    p.segs = vv_scan_num_segments(a.seqlen);
+    p.NB = a.dstate <= 8 ? 8 : (a.dstate <= 16 ? 16 : 32);
+    const int dpg = a.dim / a.ngroups;
+    p.grid = dim3(p.segs, a.ngroups * ((dpg + vv::kSegRows - 1) / vv::kSegRows), a.batch);
+    return p;
+}
+
+template <typename T, bool kVec, int NB, bool kRev>
+int launch_seg_agg(const vv_scan_args& a, const SegPlan& p, cudaStream_t st) {
+    const size_t smem = (kRev ? 3 : 2) * (size_t)vv::SegSmem<T>::kRawTile + 2 * (size_t)vv::SegSmem<T>::kF32Tile +
+                        (size_t)vv::kSeg * NB * (sizeof(float) + sizeof(T));
+    int rc;
+    if ((rc = set_smem(vv::seg_agg_kernel<T, kVec, NB, kRev>, smem)) != VV_OK) return rc;
+    vv::seg_agg_kernel<T, kVec, NB, kRev><<<p.grid, vv::kSegThreads, smem, st>>>(a);
+    return check_launch(kRev ? "seg_agg_kernel<rev>" : "seg_agg_kernel<fwd>");
+}
+
+template <typename T, bool kVec, int NB>
+int launch_seg_fwd(const vv_scan_args& a, const SegPlan& p, cudaStream_t st) {
+    const size_t smem = 3 * (size_t)vv::SegSmem<T>::kRawTile + 2 * (size_t)vv::SegSmem<T>::kF32Tile +
+                        2 * (size_t)vv::kSeg * NB * (sizeof(float) + sizeof(T));
+    int rc;
+    if ((rc = set_smem(vv::seg_fwd_kernel<T, kVec, NB>, smem)) != VV_OK) return rc;
+    vv::seg_fwd_kernel<T, kVec, NB><<<p.grid, vv::kSegThreads, smem, st>>>(a);
+    return check_launch("seg_fwd_kernel");
+}
+
+template <bool kRev>
+int launch_seg_carry(const vv_scan_args& a, const SegPlan& p, cudaStream_t st) {
+    const int64_t rows = (int64_t)a.batch * a.dim;
+    vv::seg_carry_kernel<kRev><<<(unsigned)rows, vv::kCarryThreads, 0, st>>>(
+        reinterpret_cast<const float2*>(a.agg), kRev ? a.radj : a.chk, kRev ? nullptr : a.last_state, p.segs, a.dstate);
+    return check_launch(kRev ? "seg_carry_kernel<rev>" : "seg_carry_kernel<fwd>");
+}
+
+#define VV_NB_SWITCH(NBVAL, ...)                 \
+    switch (NBVAL) {                             \
+        case 8: { constexpr int NB = 8; __VA_ARGS__; break; }   \
+        case 16: { constexpr int NB = 16; __VA_ARGS__; break; } \
+        default: { constexpr int NB = 32; __VA_ARGS__; break; } \
+    }
+
 template <typename T, bool kVec>
 int scan_fwd_t(const vv_scan_args& a, cudaStream_t st) {
-    const ScanPlan p = plan_scan(a);
-    const dim3 grid(p.units, a.dim / (p.W * p.rows_seq), a.batch);
-    const dim3 block(p.W * 32);
-    const size_t tile = (size_t)a.dstate * vv::kSlots * sizeof(float4);
-    const int64_t rows = (int64_t)a.batch * a.dim;
-    int rc;
+    const SegPlan p = plan_seg(a);
+    int rc = VV_OK;
     if (g_pass_mask & 1) {
-        vv::scan_agg_kernel<T, kVec, false><<<grid, block, tile, st>>>(a, p.rows_seq);
-        if ((rc = check_launch("scan_agg_kernel<fwd>")) != VV_OK) return rc;
+        VV_NB_SWITCH(p.NB, rc = (launch_seg_agg<T, kVec, NB, false>(a, p, st)));
+        if (rc != VV_OK) return rc;
     }
     if (g_pass_mask & 2) {
-        const int64_t chains = rows * a.dstate;
-        vv::scan_carry_kernel<false><<<(unsigned)((chains + 127) / 128), 128, 0, st>>>(
-            reinterpret_cast<const float2*>(a.agg), a.chk, a.last_state, rows, p.units, a.dstate);
-        if ((rc = check_launch("scan_carry_kernel<fwd>")) != VV_OK) return rc;
+        if ((rc = launch_seg_carry<false>(a, p, st)) != VV_OK) return rc;
     }
     if (g_pass_mask & 4) {
-        if ((rc = set_smem(vv::scan_fwd_main_kernel<T, kVec>, 2 * tile)) != VV_OK) return rc;
-        vv::scan_fwd_main_kernel<T, kVec><<<grid, block, 2 * tile, st>>>(a, p.rows_seq);
-        if ((rc = check_launch("scan_fwd_main_kernel")) != VV_OK) return rc;
+        VV_NB_SWITCH(p.NB, rc = (launch_seg_fwd<T, kVec, NB>(a, p, st)));
+        if (rc != VV_OK) return rc;
     }
     return VV_OK;
 }
 
 template <typename T, bool kVec>
 int scan_bwd_t(const vv_scan_args& a, cudaStream_t st) {
-    const ScanPlan p = plan_scan(a);
-    const dim3 grid(p.units, a.dim / (p.W * p.rows_seq), a.batch);
-    const dim3 block(p.W * 32);
-    const size_t tile = (size_t)a.dstate * vv::kSlots * sizeof(float4);
-    const int64_t rows = (int64_t)a.batch * a.dim;
-    int rc;
+    const SegPlan sp = plan_seg(a);
+    int rc = VV_OK;
     if (g_pass_mask & 1) {
-        vv::scan_agg_kernel<T, kVec, true><<<grid, block, tile, st>>>(a, p.rows_seq);
-        if ((rc = check_launch("scan_agg_kernel<rev>")) != VV_OK) return rc;
+        VV_NB_SWITCH(sp.NB, rc = (launch_seg_agg<T, kVec, NB, true>(a, sp, st)));
+        if (rc != VV_OK) return rc;
     }
     if (g_pass_mask & 2) {
-        const int64_t chains = rows * a.dstate;
-        vv::scan_carry_kernel<true><<<(unsigned)((chains + 127) / 128), 128, 0, st>>>(
-            reinterpret_cast<const float2*>(a.agg), a.radj, nullptr, rows, p.units, a.dstate);
-        if ((rc = check_launch("scan_carry_kernel<rev>")) != VV_OK) return rc;
+        if ((rc = launch_seg_carry<true>(a, sp, st)) != VV_OK) return rc;
     }
     if (g_pass_mask & 4) {
+        const ScanPlan p = plan_scan(a);
+        const dim3 grid(p.units, a.dim / (p.W * p.rows_seq), a.batch);
+        const dim3 block(p.W * 32);
+        const size_t tile = (size_t)a.dstate * vv::kSlots * sizeof(float4);
         const size_t smem = 4 * tile + (size_t)p.W * a.dstate * vv::kDaPitch * sizeof(float);
         if ((rc = set_smem(vv::scan_bwd_main_kernel<T, kVec>, smem)) != VV_OK) return rc;
         vv::scan_bwd_main_kernel<T, kVec><<<grid, block, smem, st>>>(a, p.rows_seq);
@@ -256,7 +297,7 @@ int vv_scan_set_pass_mask(int mask) {
     g_pass_mask = mask & 7;
     return prev;
 }
-int vv_scan_num_units(int seqlen) { return seqlen <= 0 ? 0 : (seqlen + VV_SCAN_UNIT - 1) / VV_SCAN_UNIT; }
+int vv_scan_num_segments(int seqlen) { return seqlen <= 0 ? 0 : (seqlen + VV_SCAN_SEGMENT - 1) / VV_SCAN_SEGMENT; }
 
 int vv_conv1d_fwd(const vv_conv1d_args* a, void* stream) { return launch_conv<false>(a, stream); }
 int vv_conv1d_bwd(const vv_conv1d_args* a, void* stream) { return launch_conv<true>(a, stream); }

@@ -2,8 +2,8 @@
 (mamba/csrc/selective_scan/selective_scan.cpp:494-497): ``fwd`` and ``bwd``.
 
 Differences from the reference, all on the private side of the autograd Functions:
-* the scan intermediate returned by ``fwd`` is the checkpoint tensor ``chk`` (B, D, units, N) of
-  states entering each 256-position unit, not the reference's (B, D, n_chunks, 2N) pairs
+* the scan intermediate returned by ``fwd`` is the checkpoint tensor ``chk`` (B, D, segments, N) of
+  states entering each 64-position segment, not the reference's (B, D, n_chunks, 2N) pairs
   (selective_scan.cpp:307-313); ``fwd`` therefore also returns ``last_state`` explicitly;
 * ``bwd`` recomputes the forward states from ``chk`` and never reads a saved ``out``.
 Served: real fp32 ``A``, input-dependent B and C ((B,N,L) or (B,G,N,L)), dstate <= 32.
@@ -27,8 +27,8 @@ def _check(cond, msg):
         raise RuntimeError(msg)
 
 
-def num_units(seqlen: int) -> int:
-    return (seqlen + _lib.VV_SCAN_UNIT - 1) // _lib.VV_SCAN_UNIT
+def num_segments(seqlen: int) -> int:
+    return (seqlen + _lib.VV_SCAN_SEGMENT - 1) // _lib.VV_SCAN_SEGMENT
 
 
 def _checks(u, delta, A, B, C, D, z, delta_bias):
@@ -90,7 +90,7 @@ def fwd(u, delta, A, B, C, D, z, delta_bias, delta_softplus, want_out=True):
     _checks(u, delta, A, B, C, D, z, delta_bias)
     batch, dim, seqlen = u.shape
     dstate = A.shape[1]
-    U = num_units(seqlen)
+    U = num_segments(seqlen)
     dev = u.device
     need_out = want_out or z is None
     out = torch.empty_like(u, memory_format=torch.contiguous_format) if need_out else None
@@ -126,7 +126,7 @@ def bwd(u, delta, A, B, C, D, z, delta_bias, dout, chk, dz, delta_softplus):
            "selective_scan bwd: dout must match u and be contiguous along seqlen")
     batch, dim, seqlen = u.shape
     dstate = A.shape[1]
-    U = num_units(seqlen)
+    U = num_segments(seqlen)
     dev = u.device
     _check(chk.shape == (batch, dim, U, dstate) and chk.dtype == torch.float32 and chk.is_contiguous(),
            "selective_scan bwd: bad checkpoint tensor")
