@@ -1,9 +1,9 @@
-// scan_seq.cuh -- channel-per-lane, time-sequential selective-scan kernels for sm_100a.
+// scan_seq.cuh -- time-sequential selective-scan kernels for sm_100a.
 //
 // Used for everything that only needs the recurrence in ONE direction: the segment aggregates
-// (forward and reverse), and the whole forward pass.  Layout:
+// (forward and reverse) and the whole forward pass.  Layout:
 //
-//   * the sequence is cut into SEGMENTS of 64 positions; a CTA (4 warps) owns 32 channels x one
+//   * the sequence is cut into SEGMENTS of 64 positions; a CTA (2 warps) owns 16 channels x one
 //     segment.  Four adjacent lanes share a channel and split its N states (N/4 each, in registers);
 //     every lane walks the 64 positions in order, so a state recurrence is one FMA chain and there
 //     is no cross-lane scan and no block barrier on the data path:
@@ -12,17 +12,20 @@
 //     plus a 2-step shuffle reduce-scatter of the y partial sums per 8 positions.  That is ~half the
 //     instructions of a warp-scan formulation.  Splitting the states over lanes (instead of one
 //     lane per channel) quadruples the warps in flight -- 5120 at the B=1 stage-1 shape -- which is
-//     what keeps the MUFU pipe fed; the kernel is bound by the MUFU.EX2 rate (16 lanes/clk/SM),
-//     not by HBM: see DESIGN.md section 5.
-//   * softplus(delta + bias) and the drive dt*u (or the gated upstream gradient) are evaluated once
-//     per (channel, position) by a pre-pass into fp32 shared tiles, not once per lane.
-//   * streamed rows (u, delta, z, dout) of the CTA's channels are staged through shared memory as
-//     [channel][64] tiles in their I/O dtype: the global side is 128-bit coalesced (a warp request
-//     covers 4 rows x 128 B), the shared side is read back transposed (lane = channel) with a
-//     16-byte row pad that makes the 128-bit reads bank-conflict free.  The gated output is written
-//     over the u tile (each thread owns its row) and leaves with the same coalesced pattern.
-//   * B / C of the segment are staged once per CTA as fp32 [position][state], so every lane reads the
-//     same address (broadcast) and the bf16->fp32 conversion is paid once per CTA.
+//     what keeps the MUFU pipe fed; these kernels are bound by the MUFU.EX2 rate (16 lanes/clk/SM)
+//     and by instruction issue, not by HBM: see DESIGN.md section 5.
+//   * pre-pass: each lane reads two 128-bit chunks of its channel's rows straight from global memory
+//     (the four lanes of a channel cover 64 contiguous bytes, so every 32-byte sector is fully
+//     used), evaluates softplus(delta + bias) and the drive dt*u (or the gated upstream gradient)
+//     ONCE per (channel, position), and parks them in fp32 shared tiles [channel][64] whose rows are
+//     padded by 16 bytes, so the 128-bit reads of the walk are bank-conflict free.
+//   * B / C of the segment are converted once per CTA to fp32 [position][state] shared tiles: every
+//     lane of a quad-column reads the same address (broadcast), and the 16-bit -> fp32 conversion
+//     is paid once per CTA instead of once per channel.
+//   * the forward kernel writes its outputs into a shared tile in the I/O dtype and flushes it with
+//     128-bit stores (a row segment of 128 bytes per 8 lanes).
+//   * shared memory is kept at <= 25 KB per CTA so that >= 9 CTAs (18 warps) are resident per SM and
+//     the 2560-CTA grid of the B=1 stage-1 shape runs in ~2 full waves.
 //
 //   pass 1  seg_agg_kernel    (P, X) of every (row, segment, state), forward or reverse
 //   pass 2  seg_carry_kernel  per row: fold the segment aggregates -> state entering each segment
@@ -36,124 +39,54 @@
 namespace vv {
 
 constexpr int kSeg = 64;                      // positions per segment
-constexpr int kSegThreads = 128;              // 4 warps per CTA
-constexpr int kSegRows = 32;                  // channels per CTA: 4 lanes per channel
+constexpr int kSegRows = 16;                  // channels per CTA
+constexpr int kSegThreads = 4 * kSegRows;     // 4 lanes per channel -> 2 warps
 constexpr int kSegPerUnit = VV_SCAN_UNIT / kSeg;
+constexpr int kF32Pitch = kSeg * 4 + 16;      // bytes per row of an fp32 [channel][64] tile (17 x 16)
 
 template <typename T> struct SegTile {
-    static constexpr int kPitch = kSeg * (int)sizeof(T) + 16;   // bytes per channel row (odd multiple of 16)
+    static constexpr int kPitch = kSeg * (int)sizeof(T) + 16;   // bytes per row of an I/O-dtype tile
 };
 
-// ---------------------------------------------------------------- tile staging
-// Asynchronous 16-byte global->shared copies (LDGSTS): a thread issues all of its copies back to
-// back without holding registers, so the DRAM latency of a tile fill is paid once, not once per
-// load->store round trip.  src_bytes == 0 zero-fills the destination (positions outside [0, L)).
-__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc, int src_bytes) {
-    const unsigned dst = (unsigned)__cvta_generic_to_shared(smem_dst);
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(dst), "l"(gsrc), "r"(src_bytes) : "memory");
-}
-__device__ __forceinline__ void cp_async_wait_all() {
-    asm volatile("cp.async.commit_group;\n" ::: "memory");
-    asm volatile("cp.async.wait_group 0;\n" ::: "memory");
-}
-
-// rows [0, nrows) of `base` (row stride ds), positions [t0, t0 + 64) -> tile[row][..] in dtype T.
-// kVec: asynchronous (finish with cp_async_wait_all + __syncthreads); else synchronous scalar loads.
-template <typename T, bool kVec>
-__device__ __forceinline__ void stage_rows_in(unsigned char* __restrict__ tile, const T* __restrict__ base, int64_t ds,
-                                              int nrows, int t0, int L) {
-    constexpr int kChunks = kSeg / 8;   // 8-element chunks per row
-    for (int idx = threadIdx.x; idx < kSegRows * kChunks; idx += blockDim.x) {
-        const int r = idx / kChunks, c = idx - r * kChunks;
-        T* dst = reinterpret_cast<T*>(tile + r * SegTile<T>::kPitch) + c * 8;
-        const int t = t0 + c * 8;
-        if (kVec) {
-            const bool ok = r < nrows && t < L;
-            const T* src = ok ? base + r * ds + t : base;
-            cp_async16(dst, src, ok ? 16 : 0);
-            if (sizeof(T) == 4) cp_async16(reinterpret_cast<unsigned char*>(dst) + 16,
-                                           reinterpret_cast<const unsigned char*>(src) + (ok ? 16 : 0), ok ? 16 : 0);
-        } else {
-#pragma unroll
-            for (int i = 0; i < 8; ++i) dst[i] = (r < nrows && t + i < L) ? base[r * ds + t + i] : from_f32<T>(0.f);
-        }
-    }
-}
-
-template <typename T, bool kVec>
-__device__ __forceinline__ void stage_rows_out(const unsigned char* __restrict__ tile, T* __restrict__ base, int64_t ds,
-                                               int nrows, int t0, int L) {
-    constexpr int kChunks = kSeg / 8;
-    for (int idx = threadIdx.x; idx < kSegRows * kChunks; idx += blockDim.x) {
-        const int r = idx / kChunks, c = idx - r * kChunks;
-        const T* src = reinterpret_cast<const T*>(tile + r * SegTile<T>::kPitch) + c * 8;
-        const int t = t0 + c * 8;
-        if (r >= nrows) continue;
-        if (kVec) {
-            if (t < L) {
-                uint4* dst = reinterpret_cast<uint4*>(base + r * ds + t);
-                dst[0] = reinterpret_cast<const uint4*>(src)[0];
-                if (sizeof(T) == 4) dst[1] = reinterpret_cast<const uint4*>(src)[1];
-            }
-        } else {
-#pragma unroll
-            for (int i = 0; i < 8; ++i)
-                if (t + i < L) base[r * ds + t + i] = src[i];
-        }
-    }
-}
-
-// 8 consecutive positions of this thread's own row of a staged tile -> fp32
+// 8 consecutive positions of a staged I/O-dtype row -> fp32
 template <typename T>
 __device__ __forceinline__ void tile_read8(const unsigned char* __restrict__ row, int c, float (&v)[8]) {
     load8_plain<T>(reinterpret_cast<const T*>(row) + c * 8, v);
 }
-template <typename T>
-__device__ __forceinline__ void tile_write8(unsigned char* __restrict__ row, int c, const float (&v)[8]) {
-    store8_vec<T>(reinterpret_cast<T*>(row) + c * 8, v);
-}
 
-// B or C of the segment.  Step 1 (asynchronous when kVec): raw rows -> stage[n][64] in dtype T.
-template <typename T, bool kVec, int NB>
-__device__ __forceinline__ void stage_state_raw(T* __restrict__ stage, const T* __restrict__ base, int64_t ns,
-                                                int N, int t0, int L) {
-    constexpr int kChunks = kSeg / 8;
-    for (int idx = threadIdx.x; idx < NB * kChunks; idx += blockDim.x) {
-        const int n = idx / kChunks, c = idx - n * kChunks;
-        T* dst = stage + n * kSeg + c * 8;
-        const int t = t0 + c * 8;
-        if (kVec) {
-            const bool ok = n < N && t < L;
-            const T* src = ok ? base + n * ns + t : base;
-            cp_async16(dst, src, ok ? 16 : 0);
-            if (sizeof(T) == 4) cp_async16(reinterpret_cast<unsigned char*>(dst) + 16,
-                                           reinterpret_cast<const unsigned char*>(src) + (ok ? 16 : 0), ok ? 16 : 0);
-        } else {
+// NQ consecutive fp32 states of one position (16-byte aligned when NQ % 4 == 0, 8-byte when NQ == 2)
+template <int NQ>
+__device__ __forceinline__ void load_states(const float* __restrict__ p, float (&v)[NQ]) {
+    if (NQ % 4 == 0) {
 #pragma unroll
-            for (int i = 0; i < 8; ++i) dst[i] = (n < N && t + i < L) ? base[n * ns + t + i] : from_f32<T>(0.f);
+        for (int k = 0; k < NQ / 4; ++k) {
+            const float4 x = reinterpret_cast<const float4*>(p)[k];
+            v[4 * k] = x.x; v[4 * k + 1] = x.y; v[4 * k + 2] = x.z; v[4 * k + 3] = x.w;
         }
+    } else {
+        const float2 x = *reinterpret_cast<const float2*>(p);
+        v[0] = x.x; v[1] = x.y;
     }
 }
-// Step 2 (after the copies landed and a barrier): stage[n][64] -> fp32 tile[position][NB].  Every lane
-// of the compute phase reads the same tile address (broadcast), and the 16-bit -> fp32 conversion
-// is paid once per CTA.
-template <typename T, int NB>
-__device__ __forceinline__ void transpose_state_tile(float* __restrict__ tile, const T* __restrict__ stage) {
+
+// B or C of the segment: global (N rows, stride ns) -> fp32 tile[position][NB] (states >= N are 0).
+template <typename T, bool kVec, int NB>
+__device__ __forceinline__ void fill_state_tile(float* __restrict__ tile, const T* __restrict__ base, int64_t ns,
+                                                int N, int t0, int L) {
     constexpr int kChunks = kSeg / 8;
-    for (int idx = threadIdx.x; idx < NB * kChunks; idx += blockDim.x) {
-        const int c = idx / NB, n = idx - c * NB;   // n fastest: shared stores spread over banks
+    for (int idx = threadIdx.x; idx < NB * kChunks; idx += kSegThreads) {
+        const int c = idx / NB, n = idx - c * NB;   // n fastest: the transposed shared stores spread over banks
         float v[8];
-        load8_plain<T>(stage + n * kSeg + c * 8, v);
+        if (n < N) {
+            load8<T, kVec>(base + n * ns, t0 + c * 8, L, v);
+        } else {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[i] = 0.f;
+        }
 #pragma unroll
         for (int i = 0; i < 8; ++i) tile[(c * 8 + i) * NB + n] = v[i];
     }
 }
-
-template <typename T> struct SegSmem {
-    static constexpr int kRawTile = kSegRows * SegTile<T>::kPitch;       // [32][64] in dtype T
-    static constexpr int kF32Pitch = kSeg * 4 + 16;                        // bytes per row of an fp32 tile
-    static constexpr int kF32Tile = kSegRows * kF32Pitch;                  // [32][64] fp32
-};
 
 struct SegCoord {
     int b, g, d0, nrows, seg, t0;   // d0: first channel of the CTA, nrows: valid channels in the CTA
@@ -173,46 +106,35 @@ __device__ __forceinline__ SegCoord seg_coord(const vv_scan_args& a) {
     return c;
 }
 
-// NQ consecutive fp32 states of one position (16-byte aligned when NQ % 4 == 0, 8-byte when NQ == 2)
-template <int NQ>
-__device__ __forceinline__ void load_states(const float* __restrict__ p, float (&v)[NQ]) {
-    if (NQ % 4 == 0) {
-#pragma unroll
-        for (int k = 0; k < NQ / 4; ++k) {
-            const float4 x = reinterpret_cast<const float4*>(p)[k];
-            v[4 * k] = x.x; v[4 * k + 1] = x.y; v[4 * k + 2] = x.z; v[4 * k + 3] = x.w;
-        }
-    } else {
-        const float2 x = *reinterpret_cast<const float2*>(p);
-        v[0] = x.x; v[1] = x.y;
-    }
-}
-
-// Pre-pass of one lane: for chunks {q, q + 4} of its channel row, dt = softplus?(raw + bias) (0 outside
-// [0, L)) and coef -> fp32 tiles.  kind 0: coef = dt * u (forward drive); kind 1: coef = dout * silu(z).
-template <typename T, int kKind>
-__device__ __forceinline__ void seg_prepass(const unsigned char* __restrict__ raw_dt, const unsigned char* __restrict__ raw_cf,
-                                            const unsigned char* __restrict__ raw_z, bool has_z,
+// Pre-pass of lane (channel row, quad q): chunks {q, q + 4} of the row.
+//   f_dt   <- softplus?(delta + bias), exactly 0 outside [0, L) (padding = scan identity)
+//   f_cf   <- kKind 0: dt * u (forward drive)          kKind 1: dout * silu(z) (gated upstream grad)
+//   raw_a / raw_b (optional, I/O dtype tiles) <- verbatim copies of the `cf` row and of the z row
+template <typename T, bool kVec, int kKind>
+__device__ __forceinline__ void seg_prepass(const T* __restrict__ g_dt, const T* __restrict__ g_cf, const T* __restrict__ g_z,
                                             unsigned char* __restrict__ f_dt, unsigned char* __restrict__ f_cf,
-                                            int q, int t0, int L, float bias, bool sp) {
+                                            unsigned char* __restrict__ raw_a, unsigned char* __restrict__ raw_b,
+                                            bool live, int q, int t0, int L, float bias, bool sp) {
 #pragma unroll
     for (int k = 0; k < 2; ++k) {
         const int ch = q + 4 * k;
-        float dt[8], cf[8];
-        tile_read8<T>(raw_dt, ch, dt);
-        tile_read8<T>(raw_cf, ch, cf);
+        const int t = live ? t0 + ch * 8 : L;   // dead rows read as padding
+        float dt[8], cf[8], zv[8];
+        load8<T, kVec>(g_dt, t, L, dt);
+        load8<T, kVec>(g_cf, t, L, cf);
+        if (g_z) load8<T, kVec>(g_z, t, L, zv);
+        if (raw_a) store8_vec<T>(reinterpret_cast<T*>(raw_a) + ch * 8, cf);
+        if (raw_b && g_z) store8_vec<T>(reinterpret_cast<T*>(raw_b) + ch * 8, zv);
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
             float v = dt[i] + bias;
             if (sp) v = softplus_f(v);
-            dt[i] = (t0 + ch * 8 + i < L) ? v : 0.f;
+            dt[i] = (t + i < L) ? v : 0.f;
         }
         if (kKind == 0) {
 #pragma unroll
             for (int i = 0; i < 8; ++i) cf[i] *= dt[i];
-        } else if (has_z) {
-            float zv[8];
-            tile_read8<T>(raw_z, ch, zv);
+        } else if (g_z) {
 #pragma unroll
             for (int i = 0; i < 8; ++i) cf[i] *= zv[i] * sigmoid_f(zv[i]);
         }
@@ -223,7 +145,7 @@ __device__ __forceinline__ void seg_prepass(const unsigned char* __restrict__ ra
 
 // ================================================================ pass 1: segment aggregates
 // Lane (channel r, quad q) owns states [q*NQ, (q+1)*NQ) of channel r, NQ = NB/4.
-// smem: [raw delta][raw coef][raw z (rev)][f32 dt][f32 coef][state tile fp32][raw state stage]
+// smem: [f32 dt][f32 coef][state tile fp32]
 // kRev = false: (P, X) of h_t = a_t h_{t-1} + dt_t B_t u_t over the segment      (uses u, B)
 // kRev = true : (P, X) of r_t = a_{t+1} r_{t+1} + g_t C_t, g = dout*silu(z)     (uses dout, z, C)
 template <typename T, bool kVec, int NB, bool kRev>
@@ -232,32 +154,26 @@ __global__ void __launch_bounds__(kSegThreads) seg_agg_kernel(const vv_scan_args
     extern __shared__ __align__(16) unsigned char smem[];
     const int L = a.seqlen, N = a.dstate;
     const SegCoord c = seg_coord(a);
-    unsigned char* t_dt = smem;
-    unsigned char* t_cf = t_dt + SegSmem<T>::kRawTile;
-    unsigned char* t_z = t_cf + SegSmem<T>::kRawTile;
-    unsigned char* f_dt = t_z + (kRev ? SegSmem<T>::kRawTile : 0);
-    unsigned char* f_cf = f_dt + SegSmem<T>::kF32Tile;
-    float* t_m = reinterpret_cast<float*>(f_cf + SegSmem<T>::kF32Tile);
-    T* t_raw = reinterpret_cast<T*>(t_m + kSeg * NB);
+    unsigned char* f_dt = smem;
+    unsigned char* f_cf = f_dt + kSegRows * kF32Pitch;
+    float* t_m = reinterpret_cast<float*>(f_cf + kSegRows * kF32Pitch);
 
-    stage_rows_in<T, kVec>(t_dt, reinterpret_cast<const T*>(a.delta) + c.b * a.delta_bs + c.d0 * a.delta_ds, a.delta_ds,
-                           c.nrows, c.t0, L);
-    if (!kRev) {
-        stage_rows_in<T, kVec>(t_cf, reinterpret_cast<const T*>(a.u) + c.b * a.u_bs + c.d0 * a.u_ds, a.u_ds, c.nrows, c.t0, L);
-        stage_state_raw<T, kVec, NB>(t_raw, reinterpret_cast<const T*>(a.Bm) + c.b * a.B_bs + c.g * a.B_gs, a.B_ns, N, c.t0, L);
-    } else {
-        stage_rows_in<T, kVec>(t_cf, reinterpret_cast<const T*>(a.dout) + c.b * a.dout_bs + c.d0 * a.dout_ds, a.dout_ds,
-                               c.nrows, c.t0, L);
-        if (a.z)
-            stage_rows_in<T, kVec>(t_z, reinterpret_cast<const T*>(a.z) + c.b * a.z_bs + c.d0 * a.z_ds, a.z_ds, c.nrows, c.t0, L);
-        stage_state_raw<T, kVec, NB>(t_raw, reinterpret_cast<const T*>(a.Cm) + c.b * a.C_bs + c.g * a.C_gs, a.C_ns, N, c.t0, L);
-    }
-    // per-lane constants are fetched while the copies are in flight
     const int r = threadIdx.x >> 2, q = threadIdx.x & 3;
     const bool live = r < c.nrows;
     const int d = c.d0 + (live ? r : 0);
     const float bias = a.delta_bias ? a.delta_bias[d] : 0.f;
     const bool sp = a.delta_softplus != 0;
+    const T* g_dt = reinterpret_cast<const T*>(a.delta) + c.b * a.delta_bs + d * a.delta_ds;
+    if (!kRev) {
+        seg_prepass<T, kVec, 0>(g_dt, reinterpret_cast<const T*>(a.u) + c.b * a.u_bs + d * a.u_ds, nullptr,
+                                f_dt + r * kF32Pitch, f_cf + r * kF32Pitch, nullptr, nullptr, live, q, c.t0, L, bias, sp);
+        fill_state_tile<T, kVec, NB>(t_m, reinterpret_cast<const T*>(a.Bm) + c.b * a.B_bs + c.g * a.B_gs, a.B_ns, N, c.t0, L);
+    } else {
+        seg_prepass<T, kVec, 1>(g_dt, reinterpret_cast<const T*>(a.dout) + c.b * a.dout_bs + d * a.dout_ds,
+                                a.z ? reinterpret_cast<const T*>(a.z) + c.b * a.z_bs + d * a.z_ds : nullptr,
+                                f_dt + r * kF32Pitch, f_cf + r * kF32Pitch, nullptr, nullptr, live, q, c.t0, L, bias, sp);
+        fill_state_tile<T, kVec, NB>(t_m, reinterpret_cast<const T*>(a.Cm) + c.b * a.C_bs + c.g * a.C_gs, a.C_ns, N, c.t0, L);
+    }
     float A2[NQ], h[NQ], dec[NQ];
 #pragma unroll
     for (int k = 0; k < NQ; ++k) {
@@ -272,23 +188,17 @@ __global__ void __launch_bounds__(kSegThreads) seg_agg_kernel(const vv_scan_args
         const int tn = c.t0 + kSeg;
         float dt_next = 0.f;
         if (tn < L) {
-            const float v = to_f32<T>(reinterpret_cast<const T*>(a.delta)[c.b * a.delta_bs + d * a.delta_ds + tn]) + bias;
+            const float v = to_f32<T>(g_dt[tn]) + bias;
             dt_next = sp ? softplus_f(v) : v;
         }
         sum_dt = dt_next;
 #pragma unroll
         for (int k = 0; k < NQ; ++k) dec[k] = exp2f(dt_next * A2[k]);
     }
-    if (kVec) cp_async_wait_all();
-    __syncthreads();
-    transpose_state_tile<T, NB>(t_m, t_raw);
-    seg_prepass<T, kRev ? 1 : 0>(t_dt + r * SegTile<T>::kPitch, t_cf + r * SegTile<T>::kPitch, t_z + r * SegTile<T>::kPitch,
-                                 a.z != nullptr, f_dt + r * SegSmem<T>::kF32Pitch, f_cf + r * SegSmem<T>::kF32Pitch,
-                                 q, c.t0, L, bias, sp);
     __syncthreads();
     if (!live) return;
-    const float4* my_dt = reinterpret_cast<const float4*>(f_dt + r * SegSmem<T>::kF32Pitch);
-    const float4* my_cf = reinterpret_cast<const float4*>(f_cf + r * SegSmem<T>::kF32Pitch);
+    const float4* my_dt = reinterpret_cast<const float4*>(f_dt + r * kF32Pitch);
+    const float4* my_cf = reinterpret_cast<const float4*>(f_cf + r * kF32Pitch);
     float dt_first = 0.f;
 #pragma unroll 2
     for (int jb = 0; jb < kSeg / 4; ++jb) {
@@ -399,30 +309,19 @@ __global__ void __launch_bounds__(kCarryThreads) seg_carry_kernel(const float2* 
 }
 
 // ================================================================ pass 3: forward outputs
-// smem: [raw delta -> pre-gate y][raw u -> gated y][raw z][f32 dt][f32 drive][B tile][C tile][raw B][raw C]
+// smem: [f32 dt][f32 drive][B tile][C tile][raw u -> gated y][raw z -> pre-gate y]
 template <typename T, bool kVec, int NB>
 __global__ void __launch_bounds__(kSegThreads) seg_fwd_kernel(const vv_scan_args a) {
     constexpr int NQ = NB / 4;
     extern __shared__ __align__(16) unsigned char smem[];
     const int L = a.seqlen, N = a.dstate;
     const SegCoord c = seg_coord(a);
-    unsigned char* t_dt = smem;
-    unsigned char* t_u = t_dt + SegSmem<T>::kRawTile;
-    unsigned char* t_z = t_u + SegSmem<T>::kRawTile;
-    unsigned char* f_dt = t_z + SegSmem<T>::kRawTile;
-    unsigned char* f_dr = f_dt + SegSmem<T>::kF32Tile;
-    float* t_B = reinterpret_cast<float*>(f_dr + SegSmem<T>::kF32Tile);
+    unsigned char* f_dt = smem;
+    unsigned char* f_dr = f_dt + kSegRows * kF32Pitch;
+    float* t_B = reinterpret_cast<float*>(f_dr + kSegRows * kF32Pitch);
     float* t_C = t_B + kSeg * NB;
-    T* raw_B = reinterpret_cast<T*>(t_C + kSeg * NB);
-    T* raw_C = raw_B + kSeg * NB;
-
-    stage_rows_in<T, kVec>(t_dt, reinterpret_cast<const T*>(a.delta) + c.b * a.delta_bs + c.d0 * a.delta_ds, a.delta_ds,
-                           c.nrows, c.t0, L);
-    stage_rows_in<T, kVec>(t_u, reinterpret_cast<const T*>(a.u) + c.b * a.u_bs + c.d0 * a.u_ds, a.u_ds, c.nrows, c.t0, L);
-    if (a.z)
-        stage_rows_in<T, kVec>(t_z, reinterpret_cast<const T*>(a.z) + c.b * a.z_bs + c.d0 * a.z_ds, a.z_ds, c.nrows, c.t0, L);
-    stage_state_raw<T, kVec, NB>(raw_B, reinterpret_cast<const T*>(a.Bm) + c.b * a.B_bs + c.g * a.B_gs, a.B_ns, N, c.t0, L);
-    stage_state_raw<T, kVec, NB>(raw_C, reinterpret_cast<const T*>(a.Cm) + c.b * a.C_bs + c.g * a.C_gs, a.C_ns, N, c.t0, L);
+    unsigned char* t_u = reinterpret_cast<unsigned char*>(t_C + kSeg * NB);
+    unsigned char* t_z = t_u + kSegRows * SegTile<T>::kPitch;
 
     const int r = threadIdx.x >> 2, q = threadIdx.x & 3;
     const bool live = r < c.nrows;
@@ -431,6 +330,13 @@ __global__ void __launch_bounds__(kSegThreads) seg_fwd_kernel(const vv_scan_args
     const float Dv = a.D ? a.D[d] : 0.f;
     const bool sp = a.delta_softplus != 0;
     const int S = gridDim.x;
+    seg_prepass<T, kVec, 0>(reinterpret_cast<const T*>(a.delta) + c.b * a.delta_bs + d * a.delta_ds,
+                            reinterpret_cast<const T*>(a.u) + c.b * a.u_bs + d * a.u_ds,
+                            a.z ? reinterpret_cast<const T*>(a.z) + c.b * a.z_bs + d * a.z_ds : nullptr,
+                            f_dt + r * kF32Pitch, f_dr + r * kF32Pitch, t_u + r * SegTile<T>::kPitch,
+                            t_z + r * SegTile<T>::kPitch, live, q, c.t0, L, bias, sp);
+    fill_state_tile<T, kVec, NB>(t_B, reinterpret_cast<const T*>(a.Bm) + c.b * a.B_bs + c.g * a.B_gs, a.B_ns, N, c.t0, L);
+    fill_state_tile<T, kVec, NB>(t_C, reinterpret_cast<const T*>(a.Cm) + c.b * a.C_bs + c.g * a.C_gs, a.C_ns, N, c.t0, L);
     float A2[NQ], h[NQ];
     {
         const float* E = a.chk + (((int64_t)c.b * a.dim + d) * S + c.seg) * N;
@@ -441,21 +347,14 @@ __global__ void __launch_bounds__(kSegThreads) seg_fwd_kernel(const vv_scan_args
             h[k] = n < N ? E[n] : 0.f;
         }
     }
-    if (kVec) cp_async_wait_all();
-    __syncthreads();
-    transpose_state_tile<T, NB>(t_B, raw_B);
-    transpose_state_tile<T, NB>(t_C, raw_C);
-    seg_prepass<T, 0>(t_dt + r * SegTile<T>::kPitch, t_u + r * SegTile<T>::kPitch, nullptr, false,
-                      f_dt + r * SegSmem<T>::kF32Pitch, f_dr + r * SegSmem<T>::kF32Pitch, q, c.t0, L, bias, sp);
     __syncthreads();
     {
-        // The raw delta / u rows are consumed; they now receive the pre-gate and the gated output.
-        T* o_pre = reinterpret_cast<T*>(t_dt + r * SegTile<T>::kPitch);
-        T* o_gate = reinterpret_cast<T*>(t_u + r * SegTile<T>::kPitch);
-        const T* my_u = reinterpret_cast<const T*>(t_u + r * SegTile<T>::kPitch);
-        const T* my_z = reinterpret_cast<const T*>(t_z + r * SegTile<T>::kPitch);
-        const float4* my_dt = reinterpret_cast<const float4*>(f_dt + r * SegSmem<T>::kF32Pitch);
-        const float4* my_dr = reinterpret_cast<const float4*>(f_dr + r * SegSmem<T>::kF32Pitch);
+        // the raw u / z rows receive the gated / pre-gate output in place: positions {2q, 2q+1} of a
+        // chunk are read and later overwritten by the same lane only
+        T* my_u = reinterpret_cast<T*>(t_u + r * SegTile<T>::kPitch);
+        T* my_z = reinterpret_cast<T*>(t_z + r * SegTile<T>::kPitch);
+        const float4* my_dt = reinterpret_cast<const float4*>(f_dt + r * kF32Pitch);
+        const float4* my_dr = reinterpret_cast<const float4*>(f_dr + r * kF32Pitch);
         const bool b1 = (q & 2) != 0, b0 = (q & 1) != 0;
 #pragma unroll 1
         for (int ch = 0; ch < kSeg / 8; ++ch) {
@@ -507,16 +406,28 @@ __global__ void __launch_bounds__(kSegThreads) seg_fwd_kernel(const vv_scan_args
             }
             fin[0] = fmaf(Dv, u0, fin[0]);
             fin[1] = fmaf(Dv, u1, fin[1]);
-            __syncwarp();   // all four lanes have read their u / z of this chunk before it is overwritten
-            if (a.out) { o_pre[p0] = from_f32<T>(fin[0]); o_pre[p0 + 1] = from_f32<T>(fin[1]); }
-            if (a.z) { o_gate[p0] = from_f32<T>(fin[0] * g0); o_gate[p0 + 1] = from_f32<T>(fin[1] * g1); }
+            if (a.out) { my_z[p0] = from_f32<T>(fin[0]); my_z[p0 + 1] = from_f32<T>(fin[1]); }
+            if (a.z) { my_u[p0] = from_f32<T>(fin[0] * g0); my_u[p0 + 1] = from_f32<T>(fin[1] * g1); }
         }
     }
-    __syncthreads();
-    if (a.out)
-        stage_rows_out<T, kVec>(t_dt, reinterpret_cast<T*>(a.out) + c.b * a.out_bs + c.d0 * a.out_ds, a.out_ds, c.nrows, c.t0, L);
-    if (a.z)
-        stage_rows_out<T, kVec>(t_u, reinterpret_cast<T*>(a.out_z) + c.b * a.outz_bs + c.d0 * a.outz_ds, a.outz_ds, c.nrows, c.t0, L);
+    __syncwarp();   // the four lanes of a channel (same warp) wrote its row; each lane now flushes two chunks of it
+    if (live) {
+        const unsigned char* my_u = t_u + r * SegTile<T>::kPitch;
+        const unsigned char* my_z = t_z + r * SegTile<T>::kPitch;
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+            const int ch = q + 4 * k;
+            float v[8];
+            if (a.out) {
+                tile_read8<T>(my_z, ch, v);
+                store8<T, kVec>(reinterpret_cast<T*>(a.out) + c.b * a.out_bs + d * a.out_ds, c.t0 + ch * 8, L, v);
+            }
+            if (a.z) {
+                tile_read8<T>(my_u, ch, v);
+                store8<T, kVec>(reinterpret_cast<T*>(a.out_z) + c.b * a.outz_bs + d * a.outz_ds, c.t0 + ch * 8, L, v);
+            }
+        }
+    }
 }
 
 }  // namespace vv

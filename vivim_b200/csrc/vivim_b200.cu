@@ -172,7 +172,7 @@ int set_smem(K kernel, size_t bytes) {
     return VV_OK;
 }
 
-// geometry of the segment kernels (scan_seq.cuh): 32 channels x one 64-position segment per CTA
+// geometry of the segment kernels (scan_seq.cuh): 16 channels x one 64-position segment per CTA
 struct SegPlan {
     int NB;        // compile-time state block: 8, 16 or 32
     int segs;
@@ -190,8 +190,7 @@ SegPlan plan_seg(const vv_scan_args& a) {
 
 template <typename T, bool kVec, int NB, bool kRev>
 int launch_seg_agg(const vv_scan_args& a, const SegPlan& p, cudaStream_t st) {
-    const size_t smem = (kRev ? 3 : 2) * (size_t)vv::SegSmem<T>::kRawTile + 2 * (size_t)vv::SegSmem<T>::kF32Tile +
-                        (size_t)vv::kSeg * NB * (sizeof(float) + sizeof(T));
+    const size_t smem = 2 * (size_t)vv::kSegRows * vv::kF32Pitch + (size_t)vv::kSeg * NB * sizeof(float);
     int rc;
     if ((rc = set_smem(vv::seg_agg_kernel<T, kVec, NB, kRev>, smem)) != VV_OK) return rc;
     vv::seg_agg_kernel<T, kVec, NB, kRev><<<p.grid, vv::kSegThreads, smem, st>>>(a);
@@ -200,8 +199,8 @@ int launch_seg_agg(const vv_scan_args& a, const SegPlan& p, cudaStream_t st) {
 
 template <typename T, bool kVec, int NB>
 int launch_seg_fwd(const vv_scan_args& a, const SegPlan& p, cudaStream_t st) {
-    const size_t smem = 3 * (size_t)vv::SegSmem<T>::kRawTile + 2 * (size_t)vv::SegSmem<T>::kF32Tile +
-                        2 * (size_t)vv::kSeg * NB * (sizeof(float) + sizeof(T));
+    const size_t smem = 2 * (size_t)vv::kSegRows * vv::kF32Pitch + 2 * (size_t)vv::kSeg * NB * sizeof(float) +
+                        2 * (size_t)vv::kSegRows * vv::SegTile<T>::kPitch;
     int rc;
     if ((rc = set_smem(vv::seg_fwd_kernel<T, kVec, NB>, smem)) != VV_OK) return rc;
     vv::seg_fwd_kernel<T, kVec, NB><<<p.grid, vv::kSegThreads, smem, st>>>(a);
