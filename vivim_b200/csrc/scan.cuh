@@ -122,6 +122,17 @@ __device__ __forceinline__ RowCoord row_coord(const vv_scan_args& a, int rows_se
 
 // ================================================================ pass 3 (backward)
 // Gradient formulas (real A, variable B and C): selective_scan_bwd_kernel.cuh:279-295, 439-453.
+//
+// Per-row inputs are software-pipelined: while a warp works on row k, the four 128-bit chunks per
+// lane of row k+1 (delta, u, dout, z) travel global->shared with cp.async into the lane's own slots,
+// and its per-row scalars (A, checkpoint, reverse carry, bias, D) sit in registers, so no row starts
+// with an exposed DRAM round trip.
+template <typename T>
+struct RowPrefetch {
+    static constexpr int kVB = 8 * (int)sizeof(T);              // bytes per lane per tensor
+    static constexpr int kWarpBytes = 4 * 32 * kVB + 32;        // + the chunk holding the next unit's first delta
+};
+
 template <typename T, bool kVec>
 __global__ void __launch_bounds__(128) scan_bwd_main_kernel(const vv_scan_args a, const int rows_seq) {
     extern __shared__ float4 smem4[];
@@ -131,44 +142,109 @@ __global__ void __launch_bounds__(128) scan_bwd_main_kernel(const vv_scan_args a
     float4* tC = tB + N * kSlots;
     float4* tdB = tC + N * kSlots;
     float4* tdC = tdB + N * kSlots;
-    float* s_dA = reinterpret_cast<float*>(tdC + N * kSlots);  // [W][N][kDaPitch]
+    unsigned char* pf_base = reinterpret_cast<unsigned char*>(tdC + N * kSlots);
     const int S = (L + kSeg - 1) / kSeg;   // chk / radj are indexed by 64-position segments
-    {
-        const RowCoord c0 = row_coord(a, rows_seq, 0);
-        fill_tile<T, kVec>(tB, reinterpret_cast<const T*>(a.Bm) + c0.b * a.B_bs + c0.g * a.B_gs, a.B_ns, N, c0.unit, L);
-        fill_tile<T, kVec>(tC, reinterpret_cast<const T*>(a.Cm) + c0.b * a.C_bs + c0.g * a.C_gs, a.C_ns, N, c0.unit, L);
-        for (int idx = threadIdx.x; idx < 2 * N * kSlots; idx += blockDim.x) tdB[idx] = make_float4(0.f, 0.f, 0.f, 0.f);
-    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    unsigned char* pf = pf_base + warp * RowPrefetch<T>::kWarpBytes;
+    constexpr int kVB = RowPrefetch<T>::kVB;
+    const int unit = blockIdx.x;
+    const int t0 = unit * kUnit + lane * kVecElems;
+    const int tn = unit * kUnit + kUnit;          // first position of the next unit
+    const int seg_first = unit * kSegPerUnit;
+    const int seg_last = min(seg_first + kSegPerUnit - 1, S - 1);
+
+    // asynchronous copy of one row's chunks into this lane's slots
+    auto prefetch_row = [&](const RowCoord& c) {
+        if (!kVec) return;
+        const T* rows[4] = {reinterpret_cast<const T*>(a.delta) + c.b * a.delta_bs + c.d * a.delta_ds,
+                            reinterpret_cast<const T*>(a.u) + c.b * a.u_bs + c.d * a.u_ds,
+                            reinterpret_cast<const T*>(a.dout) + c.b * a.dout_bs + c.d * a.dout_ds,
+                            a.z ? reinterpret_cast<const T*>(a.z) + c.b * a.z_bs + c.d * a.z_ds : nullptr};
+        const bool ok = t0 < L;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            if (rows[j] == nullptr) continue;
+            const unsigned char* src = reinterpret_cast<const unsigned char*>(ok ? rows[j] + t0 : rows[j]);
+            unsigned char* dst = pf + (j * 32 + lane) * kVB;
+            cp_async16(dst, src, ok ? 16 : 0);
+            if (kVB == 32) cp_async16(dst + 16, src + (ok ? 16 : 0), ok ? 16 : 0);
+        }
+        if (lane == 31) cp_async16(pf + 4 * 32 * kVB, tn < L ? rows[0] + tn : rows[0], tn < L ? 16 : 0);
+        cp_async_commit();
+    };
+    struct RowScalars { float A_l, E_l, R_l, bias, Dv; };
+    auto load_scalars = [&](const RowCoord& c) {
+        RowScalars s;
+        s.bias = a.delta_bias ? a.delta_bias[c.d] : 0.f;
+        s.Dv = a.D ? a.D[c.d] : 0.f;
+        s.A_l = lane < N ? a.A[c.d * a.A_ds + lane * a.A_ns] : 0.f;
+        s.E_l = lane < N ? a.chk[(c.row * S + seg_first) * N + lane] : 0.f;
+        s.R_l = lane < N ? a.radj[(c.row * S + seg_last) * N + lane] : 0.f;
+        return s;
+    };
+
+    RowCoord c = row_coord(a, rows_seq, 0);
+    prefetch_row(c);
+    RowScalars sc = load_scalars(c);
+    fill_tile<T, kVec>(tB, reinterpret_cast<const T*>(a.Bm) + c.b * a.B_bs + c.g * a.B_gs, a.B_ns, N, unit, L);
+    fill_tile<T, kVec>(tC, reinterpret_cast<const T*>(a.Cm) + c.b * a.C_bs + c.g * a.C_gs, a.C_ns, N, unit, L);
+    for (int idx = threadIdx.x; idx < 2 * N * kSlots; idx += blockDim.x) tdB[idx] = make_float4(0.f, 0.f, 0.f, 0.f);
     __syncthreads();
+
     for (int k = 0; k < rows_seq; ++k) {
-        const RowCoord c = row_coord(a, rows_seq, k);
-        const int lane = c.lane;
-        const int t0 = c.unit * kUnit + lane * kVecElems;
-        const float bias = a.delta_bias ? a.delta_bias[c.d] : 0.f;
-        const float Dv = a.D ? a.D[c.d] : 0.f;
+        const float bias = sc.bias, Dv = sc.Dv, A_l = sc.A_l, E_l = sc.E_l, R_l = sc.R_l;
+        const bool sp = a.delta_softplus != 0;
         const T* delta_row = reinterpret_cast<const T*>(a.delta) + c.b * a.delta_bs + c.d * a.delta_ds;
         float dt[8], u[8], g[8], dzf[8];
-        load_dt<T, kVec>(delta_row, t0, L, bias, a.delta_softplus != 0, dt);
-        load8<T, kVec>(reinterpret_cast<const T*>(a.u) + c.b * a.u_bs + c.d * a.u_ds, t0, L, u);
-        load8<T, kVec>(reinterpret_cast<const T*>(a.dout) + c.b * a.dout_bs + c.d * a.dout_ds, t0, L, g);
+        float dt_next = 0.f;
+        if (kVec) {
+            cp_async_wait_all();   // this lane's own slots only: no cross-lane hazard, no barrier
+            load8_plain<T>(reinterpret_cast<const T*>(pf + (0 * 32 + lane) * kVB), dt);
+            load8_plain<T>(reinterpret_cast<const T*>(pf + (1 * 32 + lane) * kVB), u);
+            load8_plain<T>(reinterpret_cast<const T*>(pf + (2 * 32 + lane) * kVB), g);
+            if (a.z) load8_plain<T>(reinterpret_cast<const T*>(pf + (3 * 32 + lane) * kVB), dzf);
+            if (lane == 31 && tn < L) dt_next = to_f32<T>(*reinterpret_cast<const T*>(pf + 4 * 32 * kVB));
+        } else {
+            load8<T, kVec>(delta_row, t0, L, dt);
+            load8<T, kVec>(reinterpret_cast<const T*>(a.u) + c.b * a.u_bs + c.d * a.u_ds, t0, L, u);
+            load8<T, kVec>(reinterpret_cast<const T*>(a.dout) + c.b * a.dout_bs + c.d * a.dout_ds, t0, L, g);
+            if (a.z) load8<T, kVec>(reinterpret_cast<const T*>(a.z) + c.b * a.z_bs + c.d * a.z_ds, t0, L, dzf);
+            if (lane == 31 && tn < L) dt_next = to_f32<T>(delta_row[tn]);
+        }
+        // rows of this warp after the current one: start their copies / scalar loads now
+        const RowCoord c_cur = c;
+        RowScalars sc_next = sc;
+        if (k + 1 < rows_seq) {
+            c = row_coord(a, rows_seq, k + 1);
+            prefetch_row(c);
+            sc_next = load_scalars(c);
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            float v = dt[i] + bias;
+            if (sp) v = softplus_f(v);
+            dt[i] = (t0 + i < L) ? v : 0.f;
+        }
         if (a.z) {
-            float zv[8];
-            load8<T, kVec>(reinterpret_cast<const T*>(a.z) + c.b * a.z_bs + c.d * a.z_ds, t0, L, zv);
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
-                const float sg = sigmoid_f(zv[i]);
-                dzf[i] = g[i] * sg * (1.f + zv[i] * (1.f - sg));  // dz = dzf * y
-                g[i] *= zv[i] * sg;                                 // grad w.r.t. pre-gate y
+                const float zv = dzf[i];
+                const float sg = sigmoid_f(zv);
+                dzf[i] = g[i] * sg * (1.f + zv * (1.f - sg));   // dz = dzf * y
+                g[i] *= zv * sg;                                  // grad w.r.t. pre-gate y
             }
         }
-        float dt_next = __shfl_down_sync(0xffffffffu, dt[0], 1);
         if (lane == 31) {
-            const int tn = t0 + kVecElems;
-            dt_next = 0.f;
             if (tn < L) {
-                const float v = to_f32<T>(delta_row[tn]) + bias;
-                dt_next = a.delta_softplus ? softplus_f(v) : v;
+                const float v = dt_next + bias;
+                dt_next = sp ? softplus_f(v) : v;
+            } else {
+                dt_next = 0.f;
             }
+        }
+        {
+            const float from_above = __shfl_down_sync(0xffffffffu, dt[0], 1);
+            if (lane != 31) dt_next = from_above;
         }
         float sum_dt = 0.f;
         float y[8], s1[8], ddt[8];
@@ -180,17 +256,11 @@ __global__ void __launch_bounds__(128) scan_bwd_main_kernel(const vv_scan_args a
             ddt[i] = 0.f;
         }
         const float sum_dt_rev = sum_dt - dt[0] + dt_next;
-        const float A_l = lane < N ? a.A[c.d * a.A_ds + lane * a.A_ns] : 0.f;
-        // state entering the unit's first segment; adjoint entering its last segment from the right
-        const int seg_first = c.unit * kSegPerUnit;
-        const int seg_last = min(seg_first + kSegPerUnit - 1, S - 1);
-        const float E_l = lane < N ? a.chk[(c.row * S + seg_first) * N + lane] : 0.f;
-        const float R_l = lane < N ? a.radj[(c.row * S + seg_last) * N + lane] : 0.f;
-        float* my_dA = s_dA + c.warp * N * kDaPitch;
+        float dA_acc = 0.f;   // lane n accumulates dA[d, n]
 
         for (int j = 0; j < N; ++j) {
             // each warp of the CTA works on a different state row between two barriers
-            int n = j + c.warp;
+            int n = j + warp;
             if (n >= N) n -= N;
             const float An = __shfl_sync(0xffffffffu, A_l, n);
             const float E = __shfl_sync(0xffffffffu, E_l, n);
@@ -199,42 +269,56 @@ __global__ void __launch_bounds__(128) scan_bwd_main_kernel(const vv_scan_args a
             float bm[8], cm[8], dec[8], hs[8];
             read_tile(tB, n, lane, bm);
             read_tile(tC, n, lane, cm);
-            // ---- forward states of the unit, seeded by the checkpoint
+            // ---- lane-local aggregates of both recurrences (h left->right, adjoint right->left)
             float X = 0.f;
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
                 dec[i] = exp2f(dt[i] * A2);
-                X = fmaf(dec[i], X, dt[i] * u[i] * bm[i]);
+                hs[i] = dt[i] * u[i] * bm[i];        // drive, replaced by the state below
+                X = fmaf(dec[i], X, hs[i]);
             }
-            float P = exp2f(A2 * sum_dt);
-            warp_scan_fwd(P, X, lane);
-            float Pex = __shfl_up_sync(0xffffffffu, P, 1);
-            float Xex = __shfl_up_sync(0xffffffffu, X, 1);
-            if (lane == 0) { Pex = 1.f; Xex = 0.f; }
-            float h = fmaf(Pex, E, Xex);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                h = fmaf(dec[i], h, dt[i] * u[i] * bm[i]);
-                hs[i] = h;
-            }
-            // ---- adjoint r_t = g_t C_t + a_{t+1} r_{t+1}, seeded by the reverse carry
             const float dec_next = exp2f(dt_next * A2);
             float RX = g[7] * cm[7];
 #pragma unroll
             for (int i = 6; i >= 0; --i) RX = fmaf(dec[i + 1], RX, g[i] * cm[i]);
+            float P = exp2f(A2 * sum_dt);
             float RP = exp2f(A2 * sum_dt_rev);
-            warp_scan_rev(RP, RX, lane);
+            // ---- the two 5-step warp scans are independent: interleave their shuffle chains
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const float Pu = __shfl_up_sync(0xffffffffu, P, o);
+                const float Xu = __shfl_up_sync(0xffffffffu, X, o);
+                const float Pd = __shfl_down_sync(0xffffffffu, RP, o);
+                const float Xd = __shfl_down_sync(0xffffffffu, RX, o);
+                if (lane >= o) {
+                    X = fmaf(P, Xu, X);
+                    P *= Pu;
+                }
+                if (lane + o < 32) {
+                    RX = fmaf(RP, Xd, RX);
+                    RP *= Pd;
+                }
+            }
+            float Pex = __shfl_up_sync(0xffffffffu, P, 1);
+            float Xex = __shfl_up_sync(0xffffffffu, X, 1);
             float RPex = __shfl_down_sync(0xffffffffu, RP, 1);
             float RXex = __shfl_down_sync(0xffffffffu, RX, 1);
+            if (lane == 0) { Pex = 1.f; Xex = 0.f; }
             if (lane == 31) { RPex = 1.f; RXex = 0.f; }
+            float h = fmaf(Pex, E, Xex);    // state entering this lane's first position
             float r = fmaf(RPex, R, RXex);  // adjoint of the position right after this lane's last one
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                h = fmaf(dec[i], h, hs[i]);
+                hs[i] = h;
+            }
             float dA_loc = 0.f;
             float dBv[8], dCv[8];
 #pragma unroll
             for (int i = 7; i >= 0; --i) {
                 r = fmaf(i == 7 ? dec_next : dec[i + 1], r, g[i] * cm[i]);
                 const float drive = dt[i] * u[i];
-                const float ah = hs[i] - drive * bm[i];  // = a_t h_{t-1}
+                const float ah = fmaf(-drive, bm[i], hs[i]);  // = a_t h_{t-1}
                 const float w = r * ah;
                 s1[i] = fmaf(r, bm[i], s1[i]);
                 ddt[i] = fmaf(An, w, ddt[i]);
@@ -243,7 +327,8 @@ __global__ void __launch_bounds__(128) scan_bwd_main_kernel(const vv_scan_args a
                 dCv[i] = g[i] * hs[i];
                 y[i] = fmaf(cm[i], hs[i], y[i]);
             }
-            my_dA[n * kDaPitch + lane] = dA_loc;
+            dA_loc = warp_sum(dA_loc);
+            if (lane == n) dA_acc += dA_loc;
             if (W > 1) __syncthreads();
             {
                 float4 v = tdB[n * kSlots + lane];
@@ -269,32 +354,26 @@ __global__ void __launch_bounds__(128) scan_bwd_main_kernel(const vv_scan_args a
             du_o[i] = fmaf(Dv, g[i], dt[i] * s1[i]);
             float dd = fmaf(u[i], s1[i], ddt[i]);
             // d softplus(v)/dv = sigmoid(v) = 1 - exp(-softplus(v)); dt == 0 marks padding
-            if (a.delta_softplus) dd *= (1.f - __expf(-dt[i]));
+            if (sp) dd *= (1.f - __expf(-dt[i]));
             ddt_o[i] = dd;
             dbias_loc += (t0 + i < L) ? dd : 0.f;
             dD_loc = fmaf(g[i], u[i], dD_loc);
         }
-        store8<T, kVec>(reinterpret_cast<T*>(a.du) + c.b * a.du_bs + c.d * a.du_ds, t0, L, du_o);
-        store8<T, kVec>(reinterpret_cast<T*>(a.ddelta) + c.b * a.ddelta_bs + c.d * a.ddelta_ds, t0, L, ddt_o);
+        store8<T, kVec>(reinterpret_cast<T*>(a.du) + c_cur.b * a.du_bs + c_cur.d * a.du_ds, t0, L, du_o);
+        store8<T, kVec>(reinterpret_cast<T*>(a.ddelta) + c_cur.b * a.ddelta_bs + c_cur.d * a.ddelta_ds, t0, L, ddt_o);
         if (a.z) {
 #pragma unroll
             for (int i = 0; i < 8; ++i) dzf[i] *= y[i];
-            store8<T, kVec>(reinterpret_cast<T*>(a.dz) + c.b * a.dz_bs + c.d * a.dz_ds, t0, L, dzf);
+            store8<T, kVec>(reinterpret_cast<T*>(a.dz) + c_cur.b * a.dz_bs + c_cur.d * a.dz_ds, t0, L, dzf);
         }
         dD_loc = warp_sum(dD_loc);
         dbias_loc = warp_sum(dbias_loc);
         if (lane == 0) {
-            if (a.dD) atomicAdd(a.dD + c.d, dD_loc);
-            if (a.ddelta_bias) atomicAdd(a.ddelta_bias + c.d, dbias_loc);
+            if (a.dD) atomicAdd(a.dD + c_cur.d, dD_loc);
+            if (a.ddelta_bias) atomicAdd(a.ddelta_bias + c_cur.d, dbias_loc);
         }
-        __syncwarp();
-        if (lane < N) {
-            float s = 0.f;
-#pragma unroll 8
-            for (int i = 0; i < 32; ++i) s += my_dA[lane * kDaPitch + i];
-            atomicAdd(a.dA + c.d * N + lane, s);
-        }
-        __syncwarp();
+        if (lane < N) atomicAdd(a.dA + c_cur.d * N + lane, dA_acc);
+        sc = sc_next;
     }
     // ---- the CTA's dB / dC partial sums -> global (fp32, 128-bit reductions)
     __syncthreads();
@@ -304,7 +383,7 @@ __global__ void __launch_bounds__(128) scan_bwd_main_kernel(const vv_scan_args a
         for (int idx = threadIdx.x; idx < N * kSlots; idx += blockDim.x) {
             const int n = idx / kSlots, s = idx - n * kSlots;
             const int l = s >> 1, half = s & 1;
-            const int t = c0.unit * kUnit + l * kVecElems + half * 4;
+            const int t = unit * kUnit + l * kVecElems + half * 4;
             const float4 vb = tdB[n * kSlots + half * 32 + l];
             const float4 vc = tdC[n * kSlots + half * 32 + l];
             float* pb = a.dB + (bc_base + n) * L + t;

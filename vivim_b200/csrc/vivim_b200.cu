@@ -256,7 +256,7 @@ int scan_bwd_t(const vv_scan_args& a, cudaStream_t st) {
         const dim3 grid(p.units, a.dim / (p.W * p.rows_seq), a.batch);
         const dim3 block(p.W * 32);
         const size_t tile = (size_t)a.dstate * vv::kSlots * sizeof(float4);
-        const size_t smem = 4 * tile + (size_t)p.W * a.dstate * vv::kDaPitch * sizeof(float);
+        const size_t smem = 4 * tile + (size_t)p.W * vv::RowPrefetch<T>::kWarpBytes;
         if ((rc = set_smem(vv::scan_bwd_main_kernel<T, kVec>, smem)) != VV_OK) return rc;
         vv::scan_bwd_main_kernel<T, kVec><<<grid, block, smem, st>>>(a, p.rows_seq);
         if ((rc = check_launch("scan_bwd_main_kernel")) != VV_OK) return rc;
