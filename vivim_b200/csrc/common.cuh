@@ -142,6 +142,50 @@ __device__ __forceinline__ void store8(T* __restrict__ row, int t0, int L, const
     }
 }
 
+// ---------------------------------------------------------------- deferred unpacking
+// Raw8 holds the 8 positions of a row segment as loaded (16 or 32 bytes of registers), so that a
+// kernel can issue ALL of its global loads first and convert later: the DRAM latency of a
+// short-lived CTA is then exposed once, not once per tensor.
+template <typename T, bool kVec> struct Raw8;
+template <typename T> struct Raw8<T, true> {
+    uint4 lo, hi;   // hi only for 4-byte T
+    __device__ __forceinline__ void load(const T* __restrict__ row, int t0, int L) {
+        lo = hi = make_uint4(0, 0, 0, 0);
+        if (t0 >= 0 && t0 < L) {
+            lo = __ldg(reinterpret_cast<const uint4*>(row + t0));
+            if (sizeof(T) == 4) hi = __ldg(reinterpret_cast<const uint4*>(row + t0) + 1);
+        }
+    }
+    __device__ __forceinline__ void unpack(float (&v)[8]) const {
+        if (sizeof(T) == 4) {
+            v[0] = __uint_as_float(lo.x); v[1] = __uint_as_float(lo.y); v[2] = __uint_as_float(lo.z); v[3] = __uint_as_float(lo.w);
+            v[4] = __uint_as_float(hi.x); v[5] = __uint_as_float(hi.y); v[6] = __uint_as_float(hi.z); v[7] = __uint_as_float(hi.w);
+        } else {
+            load8_plain<T>(reinterpret_cast<const T*>(&lo), v);
+        }
+    }
+    // verbatim 8 x T to a 16-byte aligned shared address
+    __device__ __forceinline__ void store_raw(T* dst) const {
+        reinterpret_cast<uint4*>(dst)[0] = lo;
+        if (sizeof(T) == 4) reinterpret_cast<uint4*>(dst)[1] = hi;
+    }
+};
+template <typename T> struct Raw8<T, false> {
+    float f[8];
+    __device__ __forceinline__ void load(const T* __restrict__ row, int t0, int L) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int t = t0 + i;
+            f[i] = (t >= 0 && t < L) ? to_f32<T>(row[t]) : 0.f;
+        }
+    }
+    __device__ __forceinline__ void unpack(float (&v)[8]) const {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = f[i];
+    }
+    __device__ __forceinline__ void store_raw(T* dst) const { store8_vec<T>(dst, f); }
+};
+
 // ---------------------------------------------------------------- math (fast-math forms, like the
 // reference build's --use_fast_math: mamba/setup.py:145, causal-conv1d/setup.py:143)
 __device__ __forceinline__ float sigmoid_f(float v) { return __fdividef(1.f, 1.f + __expf(-v)); }

@@ -39,7 +39,7 @@
 namespace vv {
 
 constexpr int kSeg = 64;                      // positions per segment
-constexpr int kSegRows = 16;                  // channels per CTA
+constexpr int kSegRows = 32;                  // channels per CTA
 constexpr int kSegThreads = 4 * kSegRows;     // 4 lanes per channel -> 2 warps
 constexpr int kSegPerUnit = VV_SCAN_UNIT / kSeg;
 constexpr int kF32Pitch = kSeg * 4 + 16;      // bytes per row of an fp32 [channel][64] tile (17 x 16)
@@ -70,23 +70,34 @@ __device__ __forceinline__ void load_states(const float* __restrict__ p, float (
 }
 
 // B or C of the segment: global (N rows, stride ns) -> fp32 tile[position][NB] (states >= N are 0).
+// Split in two so that the loads can be issued early and consumed late.
 template <typename T, bool kVec, int NB>
-__device__ __forceinline__ void fill_state_tile(float* __restrict__ tile, const T* __restrict__ base, int64_t ns,
-                                                int N, int t0, int L) {
-    constexpr int kChunks = kSeg / 8;
-    for (int idx = threadIdx.x; idx < NB * kChunks; idx += kSegThreads) {
-        const int c = idx / NB, n = idx - c * NB;   // n fastest: the transposed shared stores spread over banks
-        float v[8];
-        if (n < N) {
-            load8<T, kVec>(base + n * ns, t0 + c * 8, L, v);
-        } else {
+struct StateTileLoader {
+    static constexpr int kChunks = kSeg / 8;
+    static constexpr int kPer = (NB * kChunks + kSegThreads - 1) / kSegThreads;
+    Raw8<T, kVec> raw[kPer];
+    __device__ __forceinline__ void load(const T* __restrict__ base, int64_t ns, int N, int t0, int L) {
 #pragma unroll
-            for (int i = 0; i < 8; ++i) v[i] = 0.f;
+        for (int j = 0; j < kPer; ++j) {
+            const int idx = threadIdx.x + j * kSegThreads;
+            const int c = idx / NB, n = idx - c * NB;   // n fastest: the transposed shared stores spread over banks
+            raw[j].load(base + (n < N ? n : 0) * ns, (n < N && c < kChunks) ? t0 + c * 8 : L, L);
         }
-#pragma unroll
-        for (int i = 0; i < 8; ++i) tile[(c * 8 + i) * NB + n] = v[i];
     }
-}
+    __device__ __forceinline__ void store(float* __restrict__ tile) const {
+#pragma unroll
+        for (int j = 0; j < kPer; ++j) {
+            const int idx = threadIdx.x + j * kSegThreads;
+            const int c = idx / NB, n = idx - c * NB;
+            if (c < kChunks) {
+                float v[8];
+                raw[j].unpack(v);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) tile[(c * 8 + i) * NB + n] = v[i];
+            }
+        }
+    }
+};
 
 struct SegCoord {
     int b, g, d0, nrows, seg, t0;   // d0: first channel of the CTA, nrows: valid channels in the CTA
@@ -106,42 +117,55 @@ __device__ __forceinline__ SegCoord seg_coord(const vv_scan_args& a) {
     return c;
 }
 
-// Pre-pass of lane (channel row, quad q): chunks {q, q + 4} of the row.
+// Pre-pass of lane (channel row, quad q): chunks {q, q + 4} of the row.  load() issues the global
+// loads, finish() converts and writes the shared tiles:
 //   f_dt   <- softplus?(delta + bias), exactly 0 outside [0, L) (padding = scan identity)
 //   f_cf   <- kKind 0: dt * u (forward drive)          kKind 1: dout * silu(z) (gated upstream grad)
 //   raw_a / raw_b (optional, I/O dtype tiles) <- verbatim copies of the `cf` row and of the z row
 template <typename T, bool kVec, int kKind>
-__device__ __forceinline__ void seg_prepass(const T* __restrict__ g_dt, const T* __restrict__ g_cf, const T* __restrict__ g_z,
-                                            unsigned char* __restrict__ f_dt, unsigned char* __restrict__ f_cf,
-                                            unsigned char* __restrict__ raw_a, unsigned char* __restrict__ raw_b,
-                                            bool live, int q, int t0, int L, float bias, bool sp) {
+struct SegPrepass {
+    Raw8<T, kVec> r_dt[2], r_cf[2], r_z[2];
+    int t[2];
+    __device__ __forceinline__ void load(const T* __restrict__ g_dt, const T* __restrict__ g_cf, const T* __restrict__ g_z,
+                                         bool live, int q, int t0, int L) {
 #pragma unroll
-    for (int k = 0; k < 2; ++k) {
-        const int ch = q + 4 * k;
-        const int t = live ? t0 + ch * 8 : L;   // dead rows read as padding
-        float dt[8], cf[8], zv[8];
-        load8<T, kVec>(g_dt, t, L, dt);
-        load8<T, kVec>(g_cf, t, L, cf);
-        if (g_z) load8<T, kVec>(g_z, t, L, zv);
-        if (raw_a) store8_vec<T>(reinterpret_cast<T*>(raw_a) + ch * 8, cf);
-        if (raw_b && g_z) store8_vec<T>(reinterpret_cast<T*>(raw_b) + ch * 8, zv);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            float v = dt[i] + bias;
-            if (sp) v = softplus_f(v);
-            dt[i] = (t + i < L) ? v : 0.f;
+        for (int k = 0; k < 2; ++k) {
+            t[k] = live ? t0 + (q + 4 * k) * 8 : L;   // dead rows read as padding
+            r_dt[k].load(g_dt, t[k], L);
+            r_cf[k].load(g_cf, t[k], L);
+            if (g_z) r_z[k].load(g_z, t[k], L);
         }
-        if (kKind == 0) {
-#pragma unroll
-            for (int i = 0; i < 8; ++i) cf[i] *= dt[i];
-        } else if (g_z) {
-#pragma unroll
-            for (int i = 0; i < 8; ++i) cf[i] *= zv[i] * sigmoid_f(zv[i]);
-        }
-        store8_vec<float>(reinterpret_cast<float*>(f_dt) + ch * 8, dt);
-        store8_vec<float>(reinterpret_cast<float*>(f_cf) + ch * 8, cf);
     }
-}
+    __device__ __forceinline__ void finish(bool has_z, unsigned char* __restrict__ f_dt, unsigned char* __restrict__ f_cf,
+                                           unsigned char* __restrict__ raw_a, unsigned char* __restrict__ raw_b,
+                                           int q, int L, float bias, bool sp) const {
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+            const int ch = q + 4 * k;
+            float dt[8], cf[8], zv[8];
+            r_dt[k].unpack(dt);
+            r_cf[k].unpack(cf);
+            if (has_z) r_z[k].unpack(zv);
+            if (raw_a) r_cf[k].store_raw(reinterpret_cast<T*>(raw_a) + ch * 8);
+            if (raw_b && has_z) r_z[k].store_raw(reinterpret_cast<T*>(raw_b) + ch * 8);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                float v = dt[i] + bias;
+                if (sp) v = softplus_f(v);
+                dt[i] = (t[k] + i < L) ? v : 0.f;
+            }
+            if (kKind == 0) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) cf[i] *= dt[i];
+            } else if (has_z) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) cf[i] *= zv[i] * sigmoid_f(zv[i]);
+            }
+            store8_vec<float>(reinterpret_cast<float*>(f_dt) + ch * 8, dt);
+            store8_vec<float>(reinterpret_cast<float*>(f_cf) + ch * 8, cf);
+        }
+    }
+};
 
 // ================================================================ pass 1: segment aggregates
 // Lane (channel r, quad q) owns states [q*NQ, (q+1)*NQ) of channel r, NQ = NB/4.
@@ -149,7 +173,7 @@ __device__ __forceinline__ void seg_prepass(const T* __restrict__ g_dt, const T*
 // kRev = false: (P, X) of h_t = a_t h_{t-1} + dt_t B_t u_t over the segment      (uses u, B)
 // kRev = true : (P, X) of r_t = a_{t+1} r_{t+1} + g_t C_t, g = dout*silu(z)     (uses dout, z, C)
 template <typename T, bool kVec, int NB, bool kRev>
-__global__ void __launch_bounds__(kSegThreads) seg_agg_kernel(const vv_scan_args a) {
+__global__ void __launch_bounds__(kSegThreads, 9) seg_agg_kernel(const vv_scan_args a) {
     constexpr int NQ = NB / 4;
     extern __shared__ __align__(16) unsigned char smem[];
     const int L = a.seqlen, N = a.dstate;
@@ -164,16 +188,19 @@ __global__ void __launch_bounds__(kSegThreads) seg_agg_kernel(const vv_scan_args
     const float bias = a.delta_bias ? a.delta_bias[d] : 0.f;
     const bool sp = a.delta_softplus != 0;
     const T* g_dt = reinterpret_cast<const T*>(a.delta) + c.b * a.delta_bs + d * a.delta_ds;
+    // every global load of the CTA is issued before the first use, so the latencies overlap
+    SegPrepass<T, kVec, kRev ? 1 : 0> pre;
+    StateTileLoader<T, kVec, NB> st;
     if (!kRev) {
-        seg_prepass<T, kVec, 0>(g_dt, reinterpret_cast<const T*>(a.u) + c.b * a.u_bs + d * a.u_ds, nullptr,
-                                f_dt + r * kF32Pitch, f_cf + r * kF32Pitch, nullptr, nullptr, live, q, c.t0, L, bias, sp);
-        fill_state_tile<T, kVec, NB>(t_m, reinterpret_cast<const T*>(a.Bm) + c.b * a.B_bs + c.g * a.B_gs, a.B_ns, N, c.t0, L);
+        pre.load(g_dt, reinterpret_cast<const T*>(a.u) + c.b * a.u_bs + d * a.u_ds, nullptr, live, q, c.t0, L);
+        st.load(reinterpret_cast<const T*>(a.Bm) + c.b * a.B_bs + c.g * a.B_gs, a.B_ns, N, c.t0, L);
     } else {
-        seg_prepass<T, kVec, 1>(g_dt, reinterpret_cast<const T*>(a.dout) + c.b * a.dout_bs + d * a.dout_ds,
-                                a.z ? reinterpret_cast<const T*>(a.z) + c.b * a.z_bs + d * a.z_ds : nullptr,
-                                f_dt + r * kF32Pitch, f_cf + r * kF32Pitch, nullptr, nullptr, live, q, c.t0, L, bias, sp);
-        fill_state_tile<T, kVec, NB>(t_m, reinterpret_cast<const T*>(a.Cm) + c.b * a.C_bs + c.g * a.C_gs, a.C_ns, N, c.t0, L);
+        pre.load(g_dt, reinterpret_cast<const T*>(a.dout) + c.b * a.dout_bs + d * a.dout_ds,
+                 a.z ? reinterpret_cast<const T*>(a.z) + c.b * a.z_bs + d * a.z_ds : nullptr, live, q, c.t0, L);
+        st.load(reinterpret_cast<const T*>(a.Cm) + c.b * a.C_bs + c.g * a.C_gs, a.C_ns, N, c.t0, L);
     }
+    float dt_next_raw = 0.f;
+    if (kRev && c.t0 + kSeg < L) dt_next_raw = to_f32<T>(g_dt[c.t0 + kSeg]);
     float A2[NQ], h[NQ], dec[NQ];
 #pragma unroll
     for (int k = 0; k < NQ; ++k) {
@@ -185,16 +212,17 @@ __global__ void __launch_bounds__(kSegThreads) seg_agg_kernel(const vv_scan_args
     float sum_dt = 0.f;
     if (kRev) {
         // decay of the first position of the NEXT segment multiplies this segment's last position
-        const int tn = c.t0 + kSeg;
         float dt_next = 0.f;
-        if (tn < L) {
-            const float v = to_f32<T>(g_dt[tn]) + bias;
+        if (c.t0 + kSeg < L) {
+            const float v = dt_next_raw + bias;
             dt_next = sp ? softplus_f(v) : v;
         }
         sum_dt = dt_next;
 #pragma unroll
         for (int k = 0; k < NQ; ++k) dec[k] = exp2f(dt_next * A2[k]);
     }
+    st.store(t_m);
+    pre.finish(kRev && a.z != nullptr, f_dt + r * kF32Pitch, f_cf + r * kF32Pitch, nullptr, nullptr, q, L, bias, sp);
     __syncthreads();
     if (!live) return;
     const float4* my_dt = reinterpret_cast<const float4*>(f_dt + r * kF32Pitch);
@@ -330,13 +358,14 @@ __global__ void __launch_bounds__(kSegThreads) seg_fwd_kernel(const vv_scan_args
     const float Dv = a.D ? a.D[d] : 0.f;
     const bool sp = a.delta_softplus != 0;
     const int S = gridDim.x;
-    seg_prepass<T, kVec, 0>(reinterpret_cast<const T*>(a.delta) + c.b * a.delta_bs + d * a.delta_ds,
-                            reinterpret_cast<const T*>(a.u) + c.b * a.u_bs + d * a.u_ds,
-                            a.z ? reinterpret_cast<const T*>(a.z) + c.b * a.z_bs + d * a.z_ds : nullptr,
-                            f_dt + r * kF32Pitch, f_dr + r * kF32Pitch, t_u + r * SegTile<T>::kPitch,
-                            t_z + r * SegTile<T>::kPitch, live, q, c.t0, L, bias, sp);
-    fill_state_tile<T, kVec, NB>(t_B, reinterpret_cast<const T*>(a.Bm) + c.b * a.B_bs + c.g * a.B_gs, a.B_ns, N, c.t0, L);
-    fill_state_tile<T, kVec, NB>(t_C, reinterpret_cast<const T*>(a.Cm) + c.b * a.C_bs + c.g * a.C_gs, a.C_ns, N, c.t0, L);
+    // every global load of the CTA is issued before the first use, so the latencies overlap
+    SegPrepass<T, kVec, 0> pre;
+    StateTileLoader<T, kVec, NB> stB, stC;
+    pre.load(reinterpret_cast<const T*>(a.delta) + c.b * a.delta_bs + d * a.delta_ds,
+             reinterpret_cast<const T*>(a.u) + c.b * a.u_bs + d * a.u_ds,
+             a.z ? reinterpret_cast<const T*>(a.z) + c.b * a.z_bs + d * a.z_ds : nullptr, live, q, c.t0, L);
+    stB.load(reinterpret_cast<const T*>(a.Bm) + c.b * a.B_bs + c.g * a.B_gs, a.B_ns, N, c.t0, L);
+    stC.load(reinterpret_cast<const T*>(a.Cm) + c.b * a.C_bs + c.g * a.C_gs, a.C_ns, N, c.t0, L);
     float A2[NQ], h[NQ];
     {
         const float* E = a.chk + (((int64_t)c.b * a.dim + d) * S + c.seg) * N;
@@ -347,6 +376,10 @@ __global__ void __launch_bounds__(kSegThreads) seg_fwd_kernel(const vv_scan_args
             h[k] = n < N ? E[n] : 0.f;
         }
     }
+    stB.store(t_B);
+    stC.store(t_C);
+    pre.finish(a.z != nullptr, f_dt + r * kF32Pitch, f_dr + r * kF32Pitch, t_u + r * SegTile<T>::kPitch,
+               t_z + r * SegTile<T>::kPitch, q, L, bias, sp);
     __syncthreads();
     {
         // the raw u / z rows receive the gated / pre-gate output in place: positions {2q, 2q+1} of a
