@@ -272,6 +272,7 @@ def run_ours(args, rank, world, local_rank):
     import torch
     import torch.distributed as dist
     from vivim_b200 import _lib, build as vbuild
+    from vivim_b200.sharding import aggregate_throughput, max_over_ranks
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device -- the hot path has no CPU fallback")
     vbuild.build()
@@ -318,11 +319,8 @@ def run_ours(args, rank, world, local_rank):
         clk.mark()
         elapsed = time_events(lambda i: step(i + args.warmup), args.steps, torch)
         barrier()
-    if world > 1:
-        tmax = torch.tensor([elapsed], device=device, dtype=torch.float64)
-        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-        elapsed = float(tmax.item())
-    value = world * (fwd_b + bwd_b) * args.steps / elapsed / 1e9
+    elapsed = max_over_ranks(elapsed, device)
+    value = aggregate_throughput((fwd_b + bwd_b) * args.steps, world, elapsed) / 1e9
     launches = 6 * args.steps
 
     # ---- the six kernels one by one (pass mask), rotating sets, CUDA events on the launch stream
@@ -458,12 +456,10 @@ def bench_e2e(s, steps, world, device, torch, dist):
     e1.record()
     torch.cuda.synchronize()
     elapsed = e0.elapsed_time(e1) / 1e3
-    if world > 1:
-        tmax = torch.tensor([elapsed], device=device, dtype=torch.float64)
-        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-        elapsed = float(tmax.item())
+    from vivim_b200.sharding import aggregate_throughput, max_over_ranks
+    elapsed = max_over_ranks(elapsed, device)
     fwd_b, bwd_b = algo_bytes(s.t["u"].shape[0])
-    return {"value": world * (fwd_b + bwd_b) * steps / elapsed / 1e9, "unit": "GB/s", "h2d_bytes_per_step": h2d,
+    return {"value": aggregate_throughput((fwd_b + bwd_b) * steps, world, elapsed) / 1e9, "unit": "GB/s", "h2d_bytes_per_step": h2d,
             "d2h_bytes_per_step": d2h_box[0], "steps": steps, "ms_per_step": elapsed / steps * 1e3,
             "api": "mamba_ssm.ops.selective_scan_interface.selective_scan_fn + autograd backward"}
 

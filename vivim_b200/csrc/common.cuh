@@ -211,6 +211,14 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc, int
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
 
+// Programmatic dependent launch (griddepcontrol): a kernel launched with the PDL attribute may begin
+// before its stream predecessor has finished.  pdl_trigger() lets the successor's CTAs be
+// scheduled as soon as every CTA of this grid has been scheduled and called it; pdl_wait() blocks
+// until the predecessor grid has completed and its memory is visible.  Both are no-ops for a
+// kernel launched without the attribute / without a PDL successor.
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

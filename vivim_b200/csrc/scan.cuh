@@ -185,10 +185,11 @@ __global__ void __launch_bounds__(128) scan_bwd_main_kernel(const vv_scan_args a
 
     RowCoord c = row_coord(a, rows_seq, 0);
     prefetch_row(c);
-    RowScalars sc = load_scalars(c);
     fill_tile<T, kVec>(tB, reinterpret_cast<const T*>(a.Bm) + c.b * a.B_bs + c.g * a.B_gs, a.B_ns, N, unit, L);
     fill_tile<T, kVec>(tC, reinterpret_cast<const T*>(a.Cm) + c.b * a.C_bs + c.g * a.C_gs, a.C_ns, N, unit, L);
     for (int idx = threadIdx.x; idx < 2 * N * kSlots; idx += blockDim.x) tdB[idx] = make_float4(0.f, 0.f, 0.f, 0.f);
+    pdl_wait();   // radj comes from the reverse carry kernel; the fills above overlap its tail
+    RowScalars sc = load_scalars(c);
     __syncthreads();
 
     for (int k = 0; k < rows_seq; ++k) {

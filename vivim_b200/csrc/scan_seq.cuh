@@ -181,6 +181,7 @@ __global__ void __launch_bounds__(kSegThreads, 9) seg_agg_kernel(const vv_scan_a
     unsigned char* f_dt = smem;
     unsigned char* f_cf = f_dt + kSegRows * kF32Pitch;
     float* t_m = reinterpret_cast<float*>(f_cf + kSegRows * kF32Pitch);
+    pdl_trigger();
 
     const int r = threadIdx.x >> 2, q = threadIdx.x & 3;
     const bool live = r < c.nrows;
@@ -277,6 +278,8 @@ template <bool kRev>
 __global__ void __launch_bounds__(kCarryThreads) seg_carry_kernel(const float2* __restrict__ agg, float* __restrict__ carry,
                                                                   float* __restrict__ last_state, const int S, const int N) {
     __shared__ float2 s_chunk[kCarryThreads];
+    pdl_trigger();
+    pdl_wait();   // segment aggregates of the preceding kernel
     const int64_t row = blockIdx.x;
     const int chunks = kCarryThreads / N;
     const int k = threadIdx.x / N, n = threadIdx.x - k * N;
@@ -367,6 +370,7 @@ __global__ void __launch_bounds__(kSegThreads) seg_fwd_kernel(const vv_scan_args
     stB.load(reinterpret_cast<const T*>(a.Bm) + c.b * a.B_bs + c.g * a.B_gs, a.B_ns, N, c.t0, L);
     stC.load(reinterpret_cast<const T*>(a.Cm) + c.b * a.C_bs + c.g * a.C_gs, a.C_ns, N, c.t0, L);
     float A2[NQ], h[NQ];
+    pdl_wait();   // chk comes from the carry kernel; everything above overlaps its tail
     {
         const float* E = a.chk + (((int64_t)c.b * a.dim + d) * S + c.seg) * N;
 #pragma unroll

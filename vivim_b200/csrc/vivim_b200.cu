@@ -92,6 +92,29 @@ int launch_conv(const vv_conv1d_args* a, void* stream) {
     }
 }
 
+// Launch `kernel`; with pdl = true the kernel may start while its predecessor in the stream is still
+// draining (programmatic dependent launch): everything before its griddepcontrol.wait -- tile
+// fills, softplus pre-pass, shared-memory zeroing -- overlaps the predecessor's tail.
+template <typename... KArgs, typename... Args>
+void launch_kernel(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, bool pdl, Args... args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl ? 1 : 0;
+    cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
+bool use_pdl() {
+    static const bool on = env_int("VV_PDL", 1) != 0;
+    return on;
+}
+
 // ---------------------------------------------------------------- scan dispatch
 struct ScanPlan {
     int W;         // warps (= channels processed concurrently) per CTA
@@ -193,7 +216,7 @@ int launch_seg_agg(const vv_scan_args& a, const SegPlan& p, cudaStream_t st) {
     const size_t smem = 2 * (size_t)vv::kSegRows * vv::kF32Pitch + (size_t)vv::kSeg * NB * sizeof(float);
     int rc;
     if ((rc = set_smem(vv::seg_agg_kernel<T, kVec, NB, kRev>, smem)) != VV_OK) return rc;
-    vv::seg_agg_kernel<T, kVec, NB, kRev><<<p.grid, vv::kSegThreads, smem, st>>>(a);
+    launch_kernel(vv::seg_agg_kernel<T, kVec, NB, kRev>, p.grid, dim3(vv::kSegThreads), smem, st, false, a);
     return check_launch(kRev ? "seg_agg_kernel<rev>" : "seg_agg_kernel<fwd>");
 }
 
@@ -203,15 +226,16 @@ int launch_seg_fwd(const vv_scan_args& a, const SegPlan& p, cudaStream_t st) {
                         2 * (size_t)vv::kSegRows * vv::SegTile<T>::kPitch;
     int rc;
     if ((rc = set_smem(vv::seg_fwd_kernel<T, kVec, NB>, smem)) != VV_OK) return rc;
-    vv::seg_fwd_kernel<T, kVec, NB><<<p.grid, vv::kSegThreads, smem, st>>>(a);
+    launch_kernel(vv::seg_fwd_kernel<T, kVec, NB>, p.grid, dim3(vv::kSegThreads), smem, st, use_pdl() && (g_pass_mask & 2), a);
     return check_launch("seg_fwd_kernel");
 }
 
 template <bool kRev>
 int launch_seg_carry(const vv_scan_args& a, const SegPlan& p, cudaStream_t st) {
     const int64_t rows = (int64_t)a.batch * a.dim;
-    vv::seg_carry_kernel<kRev><<<(unsigned)rows, vv::kCarryThreads, 0, st>>>(
-        reinterpret_cast<const float2*>(a.agg), kRev ? a.radj : a.chk, kRev ? nullptr : a.last_state, p.segs, a.dstate);
+    launch_kernel(vv::seg_carry_kernel<kRev>, dim3((unsigned)rows), dim3(vv::kCarryThreads), 0, st,
+                  use_pdl() && (g_pass_mask & 1), reinterpret_cast<const float2*>(a.agg), kRev ? a.radj : a.chk,
+                  kRev ? (float*)nullptr : a.last_state, p.segs, a.dstate);
     return check_launch(kRev ? "seg_carry_kernel<rev>" : "seg_carry_kernel<fwd>");
 }
 
@@ -258,7 +282,7 @@ int scan_bwd_t(const vv_scan_args& a, cudaStream_t st) {
         const size_t tile = (size_t)a.dstate * vv::kSlots * sizeof(float4);
         const size_t smem = 4 * tile + (size_t)p.W * vv::RowPrefetch<T>::kWarpBytes;
         if ((rc = set_smem(vv::scan_bwd_main_kernel<T, kVec>, smem)) != VV_OK) return rc;
-        vv::scan_bwd_main_kernel<T, kVec><<<grid, block, smem, st>>>(a, p.rows_seq);
+        launch_kernel(vv::scan_bwd_main_kernel<T, kVec>, grid, block, smem, st, use_pdl() && (g_pass_mask & 2), a, p.rows_seq);
         if ((rc = check_launch("scan_bwd_main_kernel")) != VV_OK) return rc;
     }
     return VV_OK;
