@@ -42,9 +42,8 @@ enum {
 };
 
 /* Sequence positions per checkpoint segment: scan states are checkpointed / carried every 64
- * positions.  VV_SCAN_UNIT (4 segments) is the work unit of one warp in the backward main kernel. */
+ * positions; one segment x 16 channels is the work unit of a CTA in every scan kernel. */
 #define VV_SCAN_SEGMENT 64
-#define VV_SCAN_UNIT 256
 
 int vv_version(void);
 const char *vv_last_error(void);
@@ -86,7 +85,8 @@ int vv_conv1d_bwd(const vv_conv1d_args *a, void *stream);
  *   agg  : 2 * B*D*S*N floats   per-segment scan aggregates (decay product, local state)
  *   chk  : B*D*S*N floats       fwd: state entering each segment (saved for bwd)
  *                               bwd: the same tensor, read
- *   radj : B*D*S*N floats       bwd only: adjoint state entering each segment from the right
+ *   radj : B*D*S*N floats       bwd only: adjoint entering each segment from the right, already multiplied by the
+ *                               decay of the first position to its right (e_t = a_t r_t)
  * The reference's `x` intermediate (B,D,n_chunks,2N) (selective_scan.cpp:307-313) is replaced by chk.
  */
 typedef struct {

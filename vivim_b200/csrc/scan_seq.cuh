@@ -41,7 +41,6 @@ namespace vv {
 constexpr int kSeg = 64;                      // positions per segment
 constexpr int kSegRows = 32;                  // channels per CTA
 constexpr int kSegThreads = 4 * kSegRows;     // 4 lanes per channel -> 2 warps
-constexpr int kSegPerUnit = VV_SCAN_UNIT / kSeg;
 constexpr int kF32Pitch = kSeg * 4 + 16;      // bytes per row of an fp32 [channel][64] tile (17 x 16)
 
 template <typename T> struct SegTile {
@@ -171,7 +170,10 @@ struct SegPrepass {
 // Lane (channel r, quad q) owns states [q*NQ, (q+1)*NQ) of channel r, NQ = NB/4.
 // smem: [f32 dt][f32 coef][state tile fp32]
 // kRev = false: (P, X) of h_t = a_t h_{t-1} + dt_t B_t u_t over the segment      (uses u, B)
-// kRev = true : (P, X) of r_t = a_{t+1} r_{t+1} + g_t C_t, g = dout*silu(z)     (uses dout, z, C)
+// kRev = true : (P, X) of e_t = a_t (e_{t+1} + g_t C_t), g = dout*silu(z)        (uses dout, z, C)
+//               e_t = a_t r_t is the adjoint of h_t pushed through its own decay: its segment
+//               aggregate has the SAME decay product as the forward one and needs nothing from
+//               the neighbouring segment.
 template <typename T, bool kVec, int NB, bool kRev>
 __global__ void __launch_bounds__(kSegThreads, 9) seg_agg_kernel(const vv_scan_args a) {
     constexpr int NQ = NB / 4;
@@ -200,35 +202,20 @@ __global__ void __launch_bounds__(kSegThreads, 9) seg_agg_kernel(const vv_scan_a
                  a.z ? reinterpret_cast<const T*>(a.z) + c.b * a.z_bs + d * a.z_ds : nullptr, live, q, c.t0, L);
         st.load(reinterpret_cast<const T*>(a.Cm) + c.b * a.C_bs + c.g * a.C_gs, a.C_ns, N, c.t0, L);
     }
-    float dt_next_raw = 0.f;
-    if (kRev && c.t0 + kSeg < L) dt_next_raw = to_f32<T>(g_dt[c.t0 + kSeg]);
-    float A2[NQ], h[NQ], dec[NQ];
+    float A2[NQ], h[NQ];
 #pragma unroll
     for (int k = 0; k < NQ; ++k) {
         const int n = q * NQ + k;
         A2[k] = n < N ? a.A[d * a.A_ds + n * a.A_ns] * kLog2e : 0.f;
         h[k] = 0.f;
-        dec[k] = 1.f;
     }
     float sum_dt = 0.f;
-    if (kRev) {
-        // decay of the first position of the NEXT segment multiplies this segment's last position
-        float dt_next = 0.f;
-        if (c.t0 + kSeg < L) {
-            const float v = dt_next_raw + bias;
-            dt_next = sp ? softplus_f(v) : v;
-        }
-        sum_dt = dt_next;
-#pragma unroll
-        for (int k = 0; k < NQ; ++k) dec[k] = exp2f(dt_next * A2[k]);
-    }
     st.store(t_m);
     pre.finish(kRev && a.z != nullptr, f_dt + r * kF32Pitch, f_cf + r * kF32Pitch, nullptr, nullptr, q, L, bias, sp);
     __syncthreads();
     if (!live) return;
     const float4* my_dt = reinterpret_cast<const float4*>(f_dt + r * kF32Pitch);
     const float4* my_cf = reinterpret_cast<const float4*>(f_cf + r * kF32Pitch);
-    float dt_first = 0.f;
 #pragma unroll 2
     for (int jb = 0; jb < kSeg / 4; ++jb) {
         const int j = kRev ? kSeg / 4 - 1 - jb : jb;
@@ -246,16 +233,12 @@ __global__ void __launch_bounds__(kSegThreads, 9) seg_agg_kernel(const vv_scan_a
 #pragma unroll
                 for (int k = 0; k < NQ; ++k) h[k] = fmaf(exp2f(dti * A2[k]), h[k], cfs[i] * m[k]);
             } else {
-                // r_t = a_{t+1} r_{t+1} + g_t C_t ; then remember a_t for the next (earlier) position
+                // pushed adjoint e_t = a_t r_t:  e_t = a_t (e_{t+1} + g_t C_t)
 #pragma unroll
-                for (int k = 0; k < NQ; ++k) h[k] = fmaf(dec[k], h[k], cfs[i] * m[k]);
-#pragma unroll
-                for (int k = 0; k < NQ; ++k) dec[k] = exp2f(dti * A2[k]);
+                for (int k = 0; k < NQ; ++k) h[k] = exp2f(dti * A2[k]) * fmaf(cfs[i], m[k], h[k]);
             }
         }
-        if (kRev && j == 0) dt_first = dts[0];
     }
-    if (kRev) sum_dt -= dt_first;   // product of a_{t+1} over the segment
     const int S = gridDim.x;
     float2* out = reinterpret_cast<float2*>(a.agg) + (((int64_t)c.b * a.dim + d) * S + c.seg) * N;
 #pragma unroll

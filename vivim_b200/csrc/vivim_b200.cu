@@ -8,7 +8,7 @@
 
 #include "../../include/vivim_b200.h"
 #include "conv1d.cuh"
-#include "scan.cuh"
+#include "scan_bwd.cuh"
 #include "scan_seq.cuh"
 
 namespace {
@@ -116,31 +116,6 @@ bool use_pdl() {
 }
 
 // ---------------------------------------------------------------- scan dispatch
-struct ScanPlan {
-    int W;         // warps (= channels processed concurrently) per CTA
-    int rows_seq;  // channels each warp walks one after another
-    int units;
-};
-
-ScanPlan plan_scan(const vv_scan_args& a) {
-    ScanPlan p;
-    p.units = (a.seqlen + VV_SCAN_UNIT - 1) / VV_SCAN_UNIT;
-    const int dpg = a.dim / a.ngroups;
-    p.W = 1;
-    for (int w : {4, 2}) {
-        if (w <= a.dstate && dpg % w == 0) { p.W = w; break; }
-    }
-    // Largest run of channels per warp that still leaves >= 8 CTAs per SM (148 SMs) in the grid.
-    const int64_t ctas_at_1 = (int64_t)a.batch * p.units * (a.dim / p.W);
-    p.rows_seq = 1;
-    for (int r : {8, 4, 2}) {
-        if ((dpg / p.W) % r == 0 && ctas_at_1 / r >= 8 * 148) { p.rows_seq = r; break; }
-    }
-    const int forced = env_int("VV_SCAN_ROWS_SEQ", 0);
-    if (forced > 0 && (dpg / p.W) % forced == 0) p.rows_seq = forced;
-    return p;
-}
-
 int check_scan_common(const vv_scan_args* a, bool bwd) {
     if (!a) return fail(VV_ERR_BAD_ARG, "scan: null args");
     if (!a->u || !a->delta || !a->A || !a->Bm || !a->Cm) return fail(VV_ERR_BAD_ARG, "scan: u, delta, A, B, C are required");
@@ -276,14 +251,12 @@ int scan_bwd_t(const vv_scan_args& a, cudaStream_t st) {
         if ((rc = launch_seg_carry<true>(a, sp, st)) != VV_OK) return rc;
     }
     if (g_pass_mask & 4) {
-        const ScanPlan p = plan_scan(a);
-        const dim3 grid(p.units, a.dim / (p.W * p.rows_seq), a.batch);
-        const dim3 block(p.W * 32);
-        const size_t tile = (size_t)a.dstate * vv::kSlots * sizeof(float4);
-        const size_t smem = 4 * tile + (size_t)p.W * vv::RowPrefetch<T>::kWarpBytes;
-        if ((rc = set_smem(vv::scan_bwd_main_kernel<T, kVec>, smem)) != VV_OK) return rc;
-        launch_kernel(vv::scan_bwd_main_kernel<T, kVec>, grid, block, smem, st, use_pdl() && (g_pass_mask & 2), a, p.rows_seq);
-        if ((rc = check_launch("scan_bwd_main_kernel")) != VV_OK) return rc;
+        const int dpg = a.dim / a.ngroups;
+        const dim3 grid(sp.segs, a.ngroups * ((dpg + vv::kBwdRows - 1) / vv::kBwdRows), a.batch);
+        const size_t smem = vv::bwd_smem_bytes(a.dstate);
+        if ((rc = set_smem(vv::seg_bwd_kernel<T, kVec>, smem)) != VV_OK) return rc;
+        launch_kernel(vv::seg_bwd_kernel<T, kVec>, grid, dim3(vv::kBwdThreads), smem, st, use_pdl() && (g_pass_mask & 2), a);
+        if ((rc = check_launch("seg_bwd_kernel")) != VV_OK) return rc;
     }
     return VV_OK;
 }
