@@ -43,35 +43,46 @@ constexpr int kBwdSlots = kSeg / 4;                    // float4 slots per state
 
 static_assert(kSeg == 64, "a channel group is 8 lanes x 8 positions");
 
-// bytes of dynamic shared memory for N states
-__host__ __device__ constexpr size_t bwd_smem_bytes(int N) {
-    return (size_t)N * (2 * kBwdSlots * 16                    // B, C tiles (CTA)
-                        + kBwdWarps * (2 * kBwdSlots * 16     // dB, dC tiles (per warp)
-                                       + kBwdGroups * 16      // (A2, A, E, R) table (per warp)
-                                       + 32 * 4));            // dA scratch (per warp)
+// float4 units of shared memory per warp / per CTA for a state block of NB rows
+__host__ __device__ constexpr int bwd_warp_f4(int NB) { return NB * (2 * kBwdSlots + kBwdGroups + 8); }
+__host__ __device__ constexpr size_t bwd_smem_bytes(int NB) {
+    return 16 * (size_t)(2 * NB * kBwdSlots + kBwdWarps * bwd_warp_f4(NB));
+}
+
+// packed fp32 pairs (FFMA2 / FMUL2 / FADD2 of sm_100): one issue slot for two lanes of math
+__device__ __forceinline__ float2 mul2(float2 x, float2 y) { return __fmul2_rn(x, y); }
+__device__ __forceinline__ float2 add2(float2 x, float2 y) { return __fadd2_rn(x, y); }
+__device__ __forceinline__ float2 fma2(float2 x, float2 y, float2 z) { return __ffma2_rn(x, y, z); }
+__device__ __forceinline__ void acc4(float4& v, float2 lo, float2 hi) {
+    asm("add.rn.ftz.f32x2 %0, %0, %1;" : "+l"(*reinterpret_cast<unsigned long long*>(&v.x)) : "l"(*reinterpret_cast<const unsigned long long*>(&lo)));
+    asm("add.rn.ftz.f32x2 %0, %0, %1;" : "+l"(*reinterpret_cast<unsigned long long*>(&v.z)) : "l"(*reinterpret_cast<const unsigned long long*>(&hi)));
+}
+__device__ __forceinline__ float4 add4(float4 v, float2 lo, float2 hi) {
+    const float2 p = add2(make_float2(v.x, v.y), lo), q = add2(make_float2(v.z, v.w), hi);
+    return make_float4(p.x, p.y, q.x, q.y);
 }
 
 // tile[n * 16 + tb]     = positions 8 tb .. 8 tb + 3 of state row n
 // tile[n * 16 + 8 + tb] = positions 8 tb + 4 .. 8 tb + 7
-// so the 8 lanes of a channel group read 128 contiguous bytes per access.
-template <typename T, bool kVec>
+// so the 8 lanes of a channel group (a quarter warp) read 128 contiguous bytes per access.
+template <typename T, bool kVec, int NB>
 struct BwdTileLoader {
-    static constexpr int kPer = (kMaxState * 8 + kBwdThreads - 1) / kBwdThreads;
+    static constexpr int kPer = (NB * 8 + kBwdThreads - 1) / kBwdThreads;
     Raw8<T, kVec> raw[kPer];
     __device__ __forceinline__ void load(const T* __restrict__ base, int64_t ns, int N, int t0, int L) {
 #pragma unroll
         for (int j = 0; j < kPer; ++j) {
             const int idx = threadIdx.x + j * kBwdThreads;
             const int n = idx >> 3, tb = idx & 7;
-            raw[j].load(base + (n < N ? n : 0) * ns, n < N ? t0 + tb * 8 : L, L);
+            raw[j].load(base + (n < N ? n : 0) * ns, (n < N && n < NB) ? t0 + tb * 8 : L, L);   // rows >= N read as 0
         }
     }
-    __device__ __forceinline__ void store(float4* __restrict__ tile, int N) const {
+    __device__ __forceinline__ void store(float4* __restrict__ tile) const {
 #pragma unroll
         for (int j = 0; j < kPer; ++j) {
             const int idx = threadIdx.x + j * kBwdThreads;
             const int n = idx >> 3, tb = idx & 7;
-            if (n < N) {
+            if (n < NB) {
                 float v[8];
                 raw[j].unpack(v);
                 tile[n * kBwdSlots + tb] = make_float4(v[0], v[1], v[2], v[3]);
@@ -87,19 +98,19 @@ struct BwdTileLoader {
 //   w_t = e_t h_{t-1}                  (= r_t a_t h_{t-1})
 //   du = D g + dt sum_n r B            ddt = u sum_n r B + sum_n A_n w
 //   dA_n = sum_t dt w                  dB_n = sum_d r dt u          dC_n = sum_d g h
-template <typename T, bool kVec>
+// NB: compile-time state block (8, 16, 32) >= N; rows N..NB-1 are zero padding.
+template <typename T, bool kVec, int NB>
 __global__ void __launch_bounds__(kBwdThreads, 4) seg_bwd_kernel(const vv_scan_args a) {
     extern __shared__ float4 smem4[];
     const int L = a.seqlen, N = a.dstate;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int cg = lane >> 3, tb = lane & 7;
     float4* tB = smem4;
-    float4* tC = tB + N * kBwdSlots;
-    float4* wbase = tC + N * kBwdSlots + warp * (N * (2 * kBwdSlots + kBwdGroups + 8));
-    float4* tdB = wbase;
-    float4* tdC = tdB + N * kBwdSlots;
-    float4* tab = tdC + N * kBwdSlots;                           // [cg][n] = (A2, A, E, R)
-    float* dAs = reinterpret_cast<float*>(tab + kBwdGroups * N);  // [n][lane]
+    float4* tC = tB + NB * kBwdSlots;
+    float4* tdB = tC + NB * kBwdSlots + warp * bwd_warp_f4(NB);
+    float4* tdC = tdB + NB * kBwdSlots;
+    float4* tab = tdC + NB * kBwdSlots;                            // [cg][n] = (A2, A, E, R)
+    float* dAs = reinterpret_cast<float*>(tab + kBwdGroups * NB);   // [n][lane]
 
     // ---- coordinates
     const int dpg = a.dim / a.ngroups;
@@ -114,7 +125,6 @@ __global__ void __launch_bounds__(kBwdThreads, 4) seg_bwd_kernel(const vv_scan_a
     const int S = gridDim.x;
     const int t0s = seg * kSeg;
     const int t0 = live ? t0s + tb * 8 : L;   // dead channels read as padding
-    const int64_t row = (int64_t)b * a.dim + d;
 
     // ---- every global load that does not depend on the preceding kernels, issued up front
     Raw8<T, kVec> r_dt, r_u, r_g, r_z;
@@ -122,28 +132,33 @@ __global__ void __launch_bounds__(kBwdThreads, 4) seg_bwd_kernel(const vv_scan_a
     r_u.load(reinterpret_cast<const T*>(a.u) + b * a.u_bs + d * a.u_ds, t0, L);
     r_g.load(reinterpret_cast<const T*>(a.dout) + b * a.dout_bs + d * a.dout_ds, t0, L);
     if (a.z) r_z.load(reinterpret_cast<const T*>(a.z) + b * a.z_bs + d * a.z_ds, t0, L);
-    BwdTileLoader<T, kVec> lB, lC;
+    BwdTileLoader<T, kVec, NB> lB, lC;
     lB.load(reinterpret_cast<const T*>(a.Bm) + b * a.B_bs + grp * a.B_gs, a.B_ns, N, t0s, L);
     lC.load(reinterpret_cast<const T*>(a.Cm) + b * a.C_bs + grp * a.C_gs, a.C_ns, N, t0s, L);
     const float bias = a.delta_bias ? a.delta_bias[d] : 0.f;
     const float Dv = a.D ? a.D[d] : 0.f;
     const bool sp = a.delta_softplus != 0;
     // table entries this lane fills: (channel group, state) pairs o = lane, lane + 32, ...
-    float tA[(kBwdGroups * kMaxState + 31) / 32];
+    constexpr int kTab = kBwdGroups * NB / 32;
+    float tA[kTab];
+    int64_t tck[kTab];
 #pragma unroll
-    for (int j = 0; j < (kBwdGroups * kMaxState + 31) / 32; ++j) {
+    for (int j = 0; j < kTab; ++j) {
         const int o = lane + 32 * j;
-        const int c2 = o / N, n2 = o - c2 * N;
+        const int c2 = o / NB, n2 = o % NB;
         const int r2 = warp * kBwdGroups + c2;
         const int d2 = grp * dpg + off + (r2 < nrows ? r2 : 0);
-        tA[j] = (c2 < kBwdGroups) ? a.A[d2 * a.A_ds + n2 * a.A_ns] : 0.f;
+        tA[j] = n2 < N ? a.A[d2 * a.A_ds + n2 * a.A_ns] : 0.f;
+        tck[j] = (((int64_t)b * a.dim + d2) * S + seg) * N + (n2 < N ? n2 : 0);
     }
     pdl_trigger();
 
-    // ---- per-position quantities of this lane's channel (fp32, registers)
-    float dt[8], drive[8], g[8], dzf[8];
+    // ---- per-position quantities of this lane's channel (fp32 pairs, registers)
+    float2 dt2[4], drive2[4], g2[4];
+    float dzf[8];
+    float sum_dt = 0.f;
     {
-        float u[8];
+        float dt[8], u[8], g[8];
         r_dt.unpack(dt);
         r_u.unpack(u);
         r_g.unpack(g);
@@ -152,7 +167,7 @@ __global__ void __launch_bounds__(kBwdThreads, 4) seg_bwd_kernel(const vv_scan_a
             float v = dt[i] + bias;
             if (sp) v = softplus_f(v);
             dt[i] = (t0 + i < L) ? v : 0.f;   // padding = scan identity (decay 1, drive 0)
-            drive[i] = dt[i] * u[i];
+            sum_dt += dt[i];
         }
         if (a.z) {
             float zv[8];
@@ -164,60 +179,69 @@ __global__ void __launch_bounds__(kBwdThreads, 4) seg_bwd_kernel(const vv_scan_a
                 g[i] *= zv[i] * sg;                                  // grad w.r.t. pre-gate y
             }
         }
+#pragma unroll
+        for (int jp = 0; jp < 4; ++jp) {
+            dt2[jp] = make_float2(dt[2 * jp], dt[2 * jp + 1]);
+            drive2[jp] = make_float2(dt[2 * jp] * u[2 * jp], dt[2 * jp + 1] * u[2 * jp + 1]);
+            g2[jp] = make_float2(g[2 * jp], g[2 * jp + 1]);
+        }
     }
-    lB.store(tB, N);
-    lC.store(tC, N);
+    lB.store(tB);
+    lC.store(tC);
     pdl_wait();   // chk is from the forward pass, radj from the reverse carry kernel just before us
 #pragma unroll
-    for (int j = 0; j < (kBwdGroups * kMaxState + 31) / 32; ++j) {
+    for (int j = 0; j < kTab; ++j) {
         const int o = lane + 32 * j;
-        const int c2 = o / N, n2 = o - c2 * N;
-        if (c2 < kBwdGroups) {
-            const int r2 = warp * kBwdGroups + c2;
-            const int d2 = grp * dpg + off + (r2 < nrows ? r2 : 0);
-            const int64_t ck = (((int64_t)b * a.dim + d2) * S + seg) * N + n2;
-            tab[c2 * N + n2] = make_float4(tA[j] * kLog2e, tA[j], a.chk[ck], a.radj[ck]);
-        }
+        const bool ok = (o % NB) < N;
+        tab[o] = make_float4(tA[j] * kLog2e, tA[j], ok ? a.chk[tck[j]] : 0.f, ok ? a.radj[tck[j]] : 0.f);
     }
     __syncthreads();
 
-    float y[8], s1[8], ddt[8];
+    float2 y2[4], s12[4], ddt2[4];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        y[i] = 0.f;
-        s1[i] = 0.f;
-        ddt[i] = 0.f;
-    }
-    const bool hi = (lane & 16) != 0, mid = (lane & 8) != 0;
-    float4* my_d = (hi ? tdC : tdB) + (mid ? 8 : 0) + tb;
+    for (int jp = 0; jp < 4; ++jp) y2[jp] = s12[jp] = ddt2[jp] = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int k = 0; k < 2 * NB * kBwdSlots / 32; ++k) tdB[lane + 32 * k] = make_float4(0.f, 0.f, 0.f, 0.f);
+    __syncwarp();
 
+    // The four channel groups of a warp work on DIFFERENT states at any time (group cg is NB/4 states
+    // ahead of group cg-1), so their read-modify-writes of the warp's dB / dC tile never touch the
+    // same row: no atomics, no shuffles, no barrier.
 #pragma unroll 1
-    for (int n = 0; n < N; ++n) {
-        const float4 q = tab[cg * N + n];
-        const float A2 = q.x, An = q.y;
-        float bm[8], cm[8], dec[8], hs[8];
+    for (int j = 0; j < NB; ++j) {
+        const int n = (j + cg * (NB / 4)) & (NB - 1);
+        const float4 q = tab[cg * NB + n];
+        const float2 A22 = make_float2(q.x, q.x), An2 = make_float2(q.y, q.y);
+        float2 bm2[4], cm2[4], hs2[4];
+        float dec[8];
         {
-            const float4 lo = tB[n * kBwdSlots + tb], hi4 = tB[n * kBwdSlots + 8 + tb];
-            bm[0] = lo.x; bm[1] = lo.y; bm[2] = lo.z; bm[3] = lo.w;
-            bm[4] = hi4.x; bm[5] = hi4.y; bm[6] = hi4.z; bm[7] = hi4.w;
+            const float4 lo = tB[n * kBwdSlots + tb], hi = tB[n * kBwdSlots + 8 + tb];
+            bm2[0] = make_float2(lo.x, lo.y); bm2[1] = make_float2(lo.z, lo.w);
+            bm2[2] = make_float2(hi.x, hi.y); bm2[3] = make_float2(hi.z, hi.w);
         }
         {
-            const float4 lo = tC[n * kBwdSlots + tb], hi4 = tC[n * kBwdSlots + 8 + tb];
-            cm[0] = lo.x; cm[1] = lo.y; cm[2] = lo.z; cm[3] = lo.w;
-            cm[4] = hi4.x; cm[5] = hi4.y; cm[6] = hi4.z; cm[7] = hi4.w;
+            const float4 lo = tC[n * kBwdSlots + tb], hi = tC[n * kBwdSlots + 8 + tb];
+            cm2[0] = make_float2(lo.x, lo.y); cm2[1] = make_float2(lo.z, lo.w);
+            cm2[2] = make_float2(hi.x, hi.y); cm2[3] = make_float2(hi.z, hi.w);
         }
         // ---- lane-local aggregates: h left->right, pushed adjoint e right->left
-        float X = 0.f, P = 1.f;
+        float X = 0.f;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            dec[i] = exp2f(dt[i] * A2);
-            hs[i] = drive[i] * bm[i];        // drive, replaced by the state below
-            X = fmaf(dec[i], X, hs[i]);
-            P *= dec[i];
+        for (int jp = 0; jp < 4; ++jp) {
+            const float2 x2 = mul2(dt2[jp], A22);
+            dec[2 * jp] = exp2f(x2.x);
+            dec[2 * jp + 1] = exp2f(x2.y);
+            hs2[jp] = mul2(drive2[jp], bm2[jp]);        // drive, replaced by the state below
+            X = fmaf(dec[2 * jp], X, hs2[jp].x);
+            X = fmaf(dec[2 * jp + 1], X, hs2[jp].y);
         }
+        const float P = exp2f(q.x * sum_dt);            // decay product of the lane's 8 positions
         float XE = 0.f;
 #pragma unroll
-        for (int i = 7; i >= 0; --i) XE = dec[i] * fmaf(g[i], cm[i], XE);
+        for (int jp = 3; jp >= 0; --jp) {
+            XE = dec[2 * jp + 1] * fmaf(g2[jp].y, cm2[jp].y, XE);
+            XE = dec[2 * jp] * fmaf(g2[jp].x, cm2[jp].x, XE);
+        }
         // ---- two independent 3-step scans over the 8 lanes of the channel, shuffle chains interleaved
         float Pf = P, Pr = P;
 #pragma unroll
@@ -246,43 +270,45 @@ __global__ void __launch_bounds__(kBwdThreads, 4) seg_bwd_kernel(const vv_scan_a
         {
             float h = h_in;
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                h = fmaf(dec[i], h, hs[i]);
-                hs[i] = h;
+            for (int jp = 0; jp < 4; ++jp) {
+                h = fmaf(dec[2 * jp], h, hs2[jp].x);
+                hs2[jp].x = h;
+                h = fmaf(dec[2 * jp + 1], h, hs2[jp].y);
+                hs2[jp].y = h;
             }
         }
-        float dA_loc = 0.f;
-        float dBv[8], dCv[8];
+        float2 dA2 = make_float2(0.f, 0.f);
+        float2 dB2[4], dC2[4];
 #pragma unroll
-        for (int i = 7; i >= 0; --i) {
-            const float rr = fmaf(g[i], cm[i], e);     // adjoint of h_t
-            e = dec[i] * rr;
-            const float w = e * (i > 0 ? hs[i - 1] : h_in);
-            s1[i] = fmaf(rr, bm[i], s1[i]);
-            ddt[i] = fmaf(An, w, ddt[i]);
-            dA_loc = fmaf(dt[i], w, dA_loc);
-            dBv[i] = rr * drive[i];
-            dCv[i] = g[i] * hs[i];
-            y[i] = fmaf(cm[i], hs[i], y[i]);
+        for (int jp = 3; jp >= 0; --jp) {
+            float2 rr, w;
+            rr.y = fmaf(g2[jp].y, cm2[jp].y, e);        // adjoint of h at position 2 jp + 1
+            e = dec[2 * jp + 1] * rr.y;
+            w.y = e * hs2[jp].x;
+            rr.x = fmaf(g2[jp].x, cm2[jp].x, e);
+            e = dec[2 * jp] * rr.x;
+            w.x = e * (jp > 0 ? hs2[jp > 0 ? jp - 1 : 0].y : h_in);
+            s12[jp] = fma2(rr, bm2[jp], s12[jp]);
+            ddt2[jp] = fma2(An2, w, ddt2[jp]);
+            dA2 = fma2(dt2[jp], w, dA2);
+            dB2[jp] = mul2(rr, drive2[jp]);
+            dC2[jp] = mul2(g2[jp], hs2[jp]);
+            y2[jp] = fma2(cm2[jp], hs2[jp], y2[jp]);
         }
-        dAs[n * 32 + lane] = dA_loc;
-        // ---- reduce dB / dC over the 4 channels of the warp: transposing reduce-scatter.
-        // lanes 0-15 end with dB, lanes 16-31 with dC; (lane & 8) selects the half of the 8 positions.
-        float k8[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const float send = hi ? dBv[i] : dCv[i];
-            const float keep = hi ? dCv[i] : dBv[i];
-            k8[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+        dAs[n * 32 + lane] = dA2.x + dA2.y;
+        {
+            float4* pB = tdB + n * kBwdSlots + tb;
+            float4* pC = tdC + n * kBwdSlots + tb;
+            float4 b0 = pB[0], b1 = pB[8], c0 = pC[0], c1 = pC[8];
+            acc4(b0, dB2[0], dB2[1]);
+            acc4(b1, dB2[2], dB2[3]);
+            acc4(c0, dC2[0], dC2[1]);
+            acc4(c1, dC2[2], dC2[3]);
+            pB[0] = b0;
+            pB[8] = b1;
+            pC[0] = c0;
+            pC[8] = c1;
         }
-        float k4[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const float send = mid ? k8[j] : k8[4 + j];
-            const float keep = mid ? k8[4 + j] : k8[j];
-            k4[j] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
-        }
-        my_d[n * kBwdSlots] = make_float4(k4[0], k4[1], k4[2], k4[3]);
     }
 
     // ---- per-position outputs of this lane's channel
@@ -292,20 +318,24 @@ __global__ void __launch_bounds__(kBwdThreads, 4) seg_bwd_kernel(const vv_scan_a
         float dD_loc = 0.f, dbias_loc = 0.f;
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-            du_o[i] = fmaf(Dv, g[i], dt[i] * s1[i]);
-            float dd = fmaf(u[i], s1[i], ddt[i]);
+            const float dti = (i & 1) ? dt2[i >> 1].y : dt2[i >> 1].x;
+            const float gi = (i & 1) ? g2[i >> 1].y : g2[i >> 1].x;
+            const float s1i = (i & 1) ? s12[i >> 1].y : s12[i >> 1].x;
+            const float ddi = (i & 1) ? ddt2[i >> 1].y : ddt2[i >> 1].x;
+            du_o[i] = fmaf(Dv, gi, dti * s1i);
+            float dd = fmaf(u[i], s1i, ddi);
             // d softplus(v)/dv = sigmoid(v) = 1 - exp(-softplus(v)); dt == 0 marks padding
-            if (sp) dd *= (1.f - __expf(-dt[i]));
+            if (sp) dd *= (1.f - __expf(-dti));
             ddt_o[i] = dd;
             dbias_loc += (t0 + i < L) ? dd : 0.f;
-            dD_loc = fmaf(g[i], u[i], dD_loc);
+            dD_loc = fmaf(gi, u[i], dD_loc);
         }
         if (live) {
             store8<T, kVec>(reinterpret_cast<T*>(a.du) + b * a.du_bs + d * a.du_ds, t0, L, du_o);
             store8<T, kVec>(reinterpret_cast<T*>(a.ddelta) + b * a.ddelta_bs + d * a.ddelta_ds, t0, L, ddt_o);
             if (a.z) {
 #pragma unroll
-                for (int i = 0; i < 8; ++i) dzf[i] *= fmaf(Dv, u[i], y[i]);
+                for (int i = 0; i < 8; ++i) dzf[i] *= fmaf(Dv, u[i], (i & 1) ? y2[i >> 1].y : y2[i >> 1].x);
                 store8<T, kVec>(reinterpret_cast<T*>(a.dz) + b * a.dz_bs + d * a.dz_ds, t0, L, dzf);
             }
         }
@@ -321,10 +351,12 @@ __global__ void __launch_bounds__(kBwdThreads, 4) seg_bwd_kernel(const vv_scan_a
     }
     // ---- dA: sum the 8 lanes of each (channel, state) of this warp
     __syncwarp();
-    for (int o = lane; o < kBwdGroups * N; o += 32) {
-        const int c2 = o / N, n2 = o - c2 * N;
+#pragma unroll
+    for (int j = 0; j < kTab; ++j) {
+        const int o = lane + 32 * j;
+        const int c2 = o / NB, n2 = o % NB;
         const int r2 = warp * kBwdGroups + c2;
-        if (r2 < nrows) {
+        if (r2 < nrows && n2 < N) {
             const float4 p0 = *reinterpret_cast<const float4*>(dAs + n2 * 32 + c2 * 8);
             const float4 p1 = *reinterpret_cast<const float4*>(dAs + n2 * 32 + c2 * 8 + 4);
             const float sum = ((p0.x + p0.y) + (p0.z + p0.w)) + ((p1.x + p1.y) + (p1.z + p1.w));
@@ -334,29 +366,31 @@ __global__ void __launch_bounds__(kBwdThreads, 4) seg_bwd_kernel(const vv_scan_a
     // ---- the CTA's dB / dC: sum the four warp tiles -> global (fp32, 128-bit reductions)
     __syncthreads();
     {
-        const float4* w0 = tC + N * kBwdSlots;
-        const int wstride = N * (2 * kBwdSlots + kBwdGroups + 8);
+        const float4* w0 = tC + NB * kBwdSlots;
         const int64_t bc_base = ((int64_t)b * a.ngroups + grp) * N;
-        for (int idx = threadIdx.x; idx < 2 * N * kBwdSlots; idx += kBwdThreads) {
-            const int tensor = idx / (N * kBwdSlots);
-            const int rem = idx - tensor * (N * kBwdSlots);
-            const int n = rem / kBwdSlots, pc = rem - n * kBwdSlots;   // pc: 4-position chunk of the segment
+#pragma unroll
+        for (int it = 0; it < 2 * NB * kBwdSlots / kBwdThreads; ++it) {
+            const int idx = threadIdx.x + it * kBwdThreads;
+            const int tensor = idx / (NB * kBwdSlots);
+            const int n = (idx / kBwdSlots) % NB, pc = idx % kBwdSlots;   // pc: 4-position chunk of the segment
             const int slot = (pc & 1) * 8 + (pc >> 1);
             float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
             for (int w = 0; w < kBwdWarps; ++w) {
-                const float4 x = w0[w * wstride + tensor * (N * kBwdSlots) + n * kBwdSlots + slot];
-                v.x += x.x; v.y += x.y; v.z += x.z; v.w += x.w;
+                const float4 x = w0[w * bwd_warp_f4(NB) + tensor * (NB * kBwdSlots) + n * kBwdSlots + slot];
+                v = add4(v, make_float2(x.x, x.y), make_float2(x.z, x.w));
             }
             const int t = t0s + pc * 4;
-            float* p = (tensor ? a.dC : a.dB) + (bc_base + n) * L + t;
-            if (kVec) {
-                if (t < L) atomicAdd(reinterpret_cast<float4*>(p), v);
-            } else {
-                const float ev[4] = {v.x, v.y, v.z, v.w};
+            if (n < N) {
+                float* p = (tensor ? a.dC : a.dB) + (bc_base + n) * L + t;
+                if (kVec) {
+                    if (t < L) atomicAdd(reinterpret_cast<float4*>(p), v);
+                } else {
+                    const float ev[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
-                for (int k = 0; k < 4; ++k)
-                    if (t + k < L) atomicAdd(p + k, ev[k]);
+                    for (int k = 0; k < 4; ++k)
+                        if (t + k < L) atomicAdd(p + k, ev[k]);
+                }
             }
         }
     }

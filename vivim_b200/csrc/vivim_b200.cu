@@ -253,9 +253,12 @@ int scan_bwd_t(const vv_scan_args& a, cudaStream_t st) {
     if (g_pass_mask & 4) {
         const int dpg = a.dim / a.ngroups;
         const dim3 grid(sp.segs, a.ngroups * ((dpg + vv::kBwdRows - 1) / vv::kBwdRows), a.batch);
-        const size_t smem = vv::bwd_smem_bytes(a.dstate);
-        if ((rc = set_smem(vv::seg_bwd_kernel<T, kVec>, smem)) != VV_OK) return rc;
-        launch_kernel(vv::seg_bwd_kernel<T, kVec>, grid, dim3(vv::kBwdThreads), smem, st, use_pdl() && (g_pass_mask & 2), a);
+        VV_NB_SWITCH(sp.NB, {
+            const size_t smem = vv::bwd_smem_bytes(NB);
+            if ((rc = set_smem(vv::seg_bwd_kernel<T, kVec, NB>, smem)) != VV_OK) return rc;
+            launch_kernel(vv::seg_bwd_kernel<T, kVec, NB>, grid, dim3(vv::kBwdThreads), smem, st,
+                          use_pdl() && (g_pass_mask & 2), a);
+        });
         if ((rc = check_launch("seg_bwd_kernel")) != VV_OK) return rc;
     }
     return VV_OK;
