@@ -40,6 +40,10 @@ constexpr int kBwdRows = kBwdWarps * kBwdGroups;       // channels per CTA
 constexpr int kBwdThreads = kBwdWarps * 32;
 constexpr int kMaxState = 32;
 constexpr int kBwdSlots = kSeg / 4;                    // float4 slots per state row of a tile
+#ifndef VV_BWD_TRANSPOSE
+#define VV_BWD_TRANSPOSE 1
+#endif
+constexpr bool kBwdTranspose = VV_BWD_TRANSPOSE != 0;  // dB/dC over a warp's channels: shuffle reduce-scatter (1) or staggered smem RMW (0)
 
 static_assert(kSeg == 64, "a channel group is 8 lanes x 8 positions");
 
@@ -200,16 +204,20 @@ __global__ void __launch_bounds__(kBwdThreads, 4) seg_bwd_kernel(const vv_scan_a
     float2 y2[4], s12[4], ddt2[4];
 #pragma unroll
     for (int jp = 0; jp < 4; ++jp) y2[jp] = s12[jp] = ddt2[jp] = make_float2(0.f, 0.f);
+    if (!kBwdTranspose) {
 #pragma unroll
-    for (int k = 0; k < 2 * NB * kBwdSlots / 32; ++k) tdB[lane + 32 * k] = make_float4(0.f, 0.f, 0.f, 0.f);
-    __syncwarp();
+        for (int k = 0; k < 2 * NB * kBwdSlots / 32; ++k) tdB[lane + 32 * k] = make_float4(0.f, 0.f, 0.f, 0.f);
+        __syncwarp();
+    }
+    const bool hi16 = (lane & 16) != 0, mid8 = (lane & 8) != 0;
+    float4* my_d = (hi16 ? tdC : tdB) + (mid8 ? 8 : 0) + tb;
 
     // The four channel groups of a warp work on DIFFERENT states at any time (group cg is NB/4 states
     // ahead of group cg-1), so their read-modify-writes of the warp's dB / dC tile never touch the
     // same row: no atomics, no shuffles, no barrier.
 #pragma unroll 1
     for (int j = 0; j < NB; ++j) {
-        const int n = (j + cg * (NB / 4)) & (NB - 1);
+        const int n = kBwdTranspose ? j : (j + cg * (NB / 4)) & (NB - 1);
         const float4 q = tab[cg * NB + n];
         const float2 A22 = make_float2(q.x, q.x), An2 = make_float2(q.y, q.y);
         float2 bm2[4], cm2[4], hs2[4];
@@ -296,7 +304,27 @@ __global__ void __launch_bounds__(kBwdThreads, 4) seg_bwd_kernel(const vv_scan_a
             y2[jp] = fma2(cm2[jp], hs2[jp], y2[jp]);
         }
         dAs[n * 32 + lane] = dA2.x + dA2.y;
-        {
+        if (kBwdTranspose) {
+            // reduce dB / dC over the 4 channels of the warp: transposing reduce-scatter.  Lanes 0-15 end
+            // with dB, lanes 16-31 with dC; (lane & 8) selects the half of the lane's 8 positions.
+            float2 k2[4];
+#pragma unroll
+            for (int jp = 0; jp < 4; ++jp) {
+                const float2 send = hi16 ? dB2[jp] : dC2[jp];
+                const float2 keep = hi16 ? dC2[jp] : dB2[jp];
+                k2[jp].x = keep.x + __shfl_xor_sync(0xffffffffu, send.x, 16);
+                k2[jp].y = keep.y + __shfl_xor_sync(0xffffffffu, send.y, 16);
+            }
+            float2 k1[2];
+#pragma unroll
+            for (int jp = 0; jp < 2; ++jp) {
+                const float2 send = mid8 ? k2[jp] : k2[2 + jp];
+                const float2 keep = mid8 ? k2[2 + jp] : k2[jp];
+                k1[jp].x = keep.x + __shfl_xor_sync(0xffffffffu, send.x, 8);
+                k1[jp].y = keep.y + __shfl_xor_sync(0xffffffffu, send.y, 8);
+            }
+            my_d[n * kBwdSlots] = make_float4(k1[0].x, k1[0].y, k1[1].x, k1[1].y);
+        } else {
             float4* pB = tdB + n * kBwdSlots + tb;
             float4* pC = tdC + n * kBwdSlots + tb;
             float4 b0 = pB[0], b1 = pB[8], c0 = pC[0], c1 = pC[8];
