@@ -169,6 +169,12 @@ template <typename T> struct Raw8<T, true> {
         reinterpret_cast<uint4*>(dst)[0] = lo;
         if (sizeof(T) == 4) reinterpret_cast<uint4*>(dst)[1] = hi;
     }
+    // Hide the register contents from the optimiser: a later unpack() is recomputed from the packed
+    // registers instead of keeping the 8 unpacked values alive in between.
+    __device__ __forceinline__ void keep_packed() {
+        asm volatile("" : "+r"(lo.x), "+r"(lo.y), "+r"(lo.z), "+r"(lo.w));
+        if (sizeof(T) == 4) asm volatile("" : "+r"(hi.x), "+r"(hi.y), "+r"(hi.z), "+r"(hi.w));
+    }
 };
 template <typename T> struct Raw8<T, false> {
     float f[8];
@@ -184,6 +190,7 @@ template <typename T> struct Raw8<T, false> {
         for (int i = 0; i < 8; ++i) v[i] = f[i];
     }
     __device__ __forceinline__ void store_raw(T* dst) const { store8_vec<T>(dst, f); }
+    __device__ __forceinline__ void keep_packed() {}
 };
 
 // ---------------------------------------------------------------- math (fast-math forms, like the

@@ -113,8 +113,9 @@ __global__ void __launch_bounds__(kBwdThreads, 4) seg_bwd_kernel(const vv_scan_a
     float4* tC = tB + NB * kBwdSlots;
     float4* tdB = tC + NB * kBwdSlots + warp * bwd_warp_f4(NB);
     float4* tdC = tdB + NB * kBwdSlots;
-    float4* tab = tdC + NB * kBwdSlots;                            // [cg][n] = (A2, A, E, R)
-    float* dAs = reinterpret_cast<float*>(tab + kBwdGroups * NB);   // [n][lane]
+    float2* tabER = reinterpret_cast<float2*>(tdC + NB * kBwdSlots);   // [cg][n] = (state entering, pushed adjoint entering)
+    float* tabA = reinterpret_cast<float*>(tabER + kBwdGroups * NB);   // [cg][n] = A * log2(e)
+    float* dAs = reinterpret_cast<float*>(tdC + NB * kBwdSlots + kBwdGroups * NB);   // [n][lane rotated by 8 n]
 
     // ---- coordinates
     const int dpg = a.dim / a.ngroups;
@@ -144,7 +145,7 @@ __global__ void __launch_bounds__(kBwdThreads, 4) seg_bwd_kernel(const vv_scan_a
     const bool sp = a.delta_softplus != 0;
     // table entries this lane fills: (channel group, state) pairs o = lane, lane + 32, ...
     constexpr int kTab = kBwdGroups * NB / 32;
-    float tA[kTab];
+    float tA[kTab], tE[kTab];
     int64_t tck[kTab];
 #pragma unroll
     for (int j = 0; j < kTab; ++j) {
@@ -154,6 +155,7 @@ __global__ void __launch_bounds__(kBwdThreads, 4) seg_bwd_kernel(const vv_scan_a
         const int d2 = grp * dpg + off + (r2 < nrows ? r2 : 0);
         tA[j] = n2 < N ? a.A[d2 * a.A_ds + n2 * a.A_ns] : 0.f;
         tck[j] = (((int64_t)b * a.dim + d2) * S + seg) * N + (n2 < N ? n2 : 0);
+        tE[j] = n2 < N ? a.chk[tck[j]] : 0.f;   // written by the forward pass: no dependency on the predecessor kernel
     }
     pdl_trigger();
 
@@ -196,8 +198,8 @@ __global__ void __launch_bounds__(kBwdThreads, 4) seg_bwd_kernel(const vv_scan_a
 #pragma unroll
     for (int j = 0; j < kTab; ++j) {
         const int o = lane + 32 * j;
-        const bool ok = (o % NB) < N;
-        tab[o] = make_float4(tA[j] * kLog2e, tA[j], ok ? a.chk[tck[j]] : 0.f, ok ? a.radj[tck[j]] : 0.f);
+        tabA[o] = tA[j] * kLog2e;
+        tabER[o] = make_float2(tE[j], (o % NB) < N ? a.radj[tck[j]] : 0.f);
     }
     __syncthreads();
 
@@ -215,11 +217,15 @@ __global__ void __launch_bounds__(kBwdThreads, 4) seg_bwd_kernel(const vv_scan_a
     // The four channel groups of a warp work on DIFFERENT states at any time (group cg is NB/4 states
     // ahead of group cg-1), so their read-modify-writes of the warp's dB / dC tile never touch the
     // same row: no atomics, no shuffles, no barrier.
+    float A2_next = tabA[cg * NB + (kBwdTranspose ? 0 : (cg * (NB / 4)) & (NB - 1))];
 #pragma unroll 1
     for (int j = 0; j < NB; ++j) {
         const int n = kBwdTranspose ? j : (j + cg * (NB / 4)) & (NB - 1);
-        const float4 q = tab[cg * NB + n];
-        const float2 A22 = make_float2(q.x, q.x), An2 = make_float2(q.y, q.y);
+        const float A2 = A2_next;
+        A2_next = tabA[cg * NB + ((n + 1) & (NB - 1))];   // one iteration ahead: the load latency is off the critical path
+        const float2 er = tabER[cg * NB + n];
+        const float An = A2 * (1.f / kLog2e);
+        const float2 A22 = make_float2(A2, A2), An2 = make_float2(An, An);
         float2 bm2[4], cm2[4], hs2[4];
         float dec[8];
         {
@@ -243,7 +249,7 @@ __global__ void __launch_bounds__(kBwdThreads, 4) seg_bwd_kernel(const vv_scan_a
             X = fmaf(dec[2 * jp], X, hs2[jp].x);
             X = fmaf(dec[2 * jp + 1], X, hs2[jp].y);
         }
-        const float P = exp2f(q.x * sum_dt);            // decay product of the lane's 8 positions
+        const float P = exp2f(A2 * sum_dt);            // decay product of the lane's 8 positions
         float XE = 0.f;
 #pragma unroll
         for (int jp = 3; jp >= 0; --jp) {
@@ -273,8 +279,8 @@ __global__ void __launch_bounds__(kBwdThreads, 4) seg_bwd_kernel(const vv_scan_a
         float XEx = __shfl_down_sync(0xffffffffu, XE, 1, 8);
         if (tb == 0) { Pfx = 1.f; Xx = 0.f; }
         if (tb == 7) { Prx = 1.f; XEx = 0.f; }
-        const float h_in = fmaf(Pfx, q.z, Xx);    // state entering this lane's first position
-        float e = fmaf(Prx, q.w, XEx);            // pushed adjoint entering from the right
+        const float h_in = fmaf(Pfx, er.x, Xx);    // state entering this lane's first position
+        float e = fmaf(Prx, er.y, XEx);            // pushed adjoint entering from the right
         {
             float h = h_in;
 #pragma unroll
@@ -303,7 +309,7 @@ __global__ void __launch_bounds__(kBwdThreads, 4) seg_bwd_kernel(const vv_scan_a
             dC2[jp] = mul2(g2[jp], hs2[jp]);
             y2[jp] = fma2(cm2[jp], hs2[jp], y2[jp]);
         }
-        dAs[n * 32 + lane] = dA2.x + dA2.y;
+        dAs[n * 32 + ((lane + 8 * n) & 31)] = dA2.x + dA2.y;
         if (kBwdTranspose) {
             // reduce dB / dC over the 4 channels of the warp: transposing reduce-scatter.  Lanes 0-15 end
             // with dB, lanes 16-31 with dC; (lane & 8) selects the half of the lane's 8 positions.
@@ -342,6 +348,7 @@ __global__ void __launch_bounds__(kBwdThreads, 4) seg_bwd_kernel(const vv_scan_a
     // ---- per-position outputs of this lane's channel
     {
         float u[8], du_o[8], ddt_o[8];
+        r_u.keep_packed();
         r_u.unpack(u);
         float dD_loc = 0.f, dbias_loc = 0.f;
 #pragma unroll
@@ -385,8 +392,9 @@ __global__ void __launch_bounds__(kBwdThreads, 4) seg_bwd_kernel(const vv_scan_a
         const int c2 = o / NB, n2 = o % NB;
         const int r2 = warp * kBwdGroups + c2;
         if (r2 < nrows && n2 < N) {
-            const float4 p0 = *reinterpret_cast<const float4*>(dAs + n2 * 32 + c2 * 8);
-            const float4 p1 = *reinterpret_cast<const float4*>(dAs + n2 * 32 + c2 * 8 + 4);
+            const float* src = dAs + n2 * 32 + ((c2 * 8 + 8 * n2) & 31);
+            const float4 p0 = *reinterpret_cast<const float4*>(src);
+            const float4 p1 = *reinterpret_cast<const float4*>(src + 4);
             const float sum = ((p0.x + p0.y) + (p0.z + p0.w)) + ((p1.x + p1.y) + (p1.z + p1.w));
             atomicAdd(a.dA + (int64_t)(grp * dpg + off + r2) * N + n2, sum);
         }
@@ -400,8 +408,8 @@ __global__ void __launch_bounds__(kBwdThreads, 4) seg_bwd_kernel(const vv_scan_a
         for (int it = 0; it < 2 * NB * kBwdSlots / kBwdThreads; ++it) {
             const int idx = threadIdx.x + it * kBwdThreads;
             const int tensor = idx / (NB * kBwdSlots);
-            const int n = (idx / kBwdSlots) % NB, pc = idx % kBwdSlots;   // pc: 4-position chunk of the segment
-            const int slot = (pc & 1) * 8 + (pc >> 1);
+            const int n = (idx / kBwdSlots) % NB, slot = idx % kBwdSlots;   // consecutive threads, consecutive slots
+            const int pc = (slot & 7) * 2 + (slot >> 3);                      // the 4-position chunk of the segment it holds
             float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
             for (int w = 0; w < kBwdWarps; ++w) {
