@@ -359,7 +359,7 @@ def run_ours(args, rank, world, local_rank):
     # ---- end to end: public API, host (pinned) buffers in, all results out, every step
     e2e_steps = max(4, min(args.steps, 40))
     e2e = bench_e2e(sets[0], e2e_steps, world, device, torch, dist)
-    launches += 6 * (e2e_steps + 4)
+    launches += 6 * (3 * e2e_steps + 4)
 
     if rank != 0:
         if world > 1:
@@ -471,24 +471,31 @@ def bench_e2e(s, steps, world, device, torch, dist):
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()                                     # current stream; the three streams start after it
-    for st in (s_in, s_cmp, s_out):
-        st.wait_event(e0)
-    for i in range(steps):
-        one(i)
-    cur = torch.cuda.current_stream()
-    for st in (s_in, s_cmp, s_out):
-        done = torch.cuda.Event()
-        done.record(st)
-        cur.wait_event(done)
-    e1.record()
-    torch.cuda.synchronize()
-    elapsed = e0.elapsed_time(e1) / 1e3
+    def block():
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()                                 # current stream; the three streams start after it
+        for st in (s_in, s_cmp, s_out):
+            st.wait_event(e0)
+        for i in range(steps):
+            one(i)
+        cur = torch.cuda.current_stream()
+        for st in (s_in, s_cmp, s_out):
+            done = torch.cuda.Event()
+            done.record(st)
+            cur.wait_event(done)
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / 1e3
+
+    # three timed blocks of `steps` steps; the median block is reported (the host side of this path is
+    # Python + autograd, and a single block is at the mercy of one scheduling hiccup on the box)
+    blocks = sorted(block() for _ in range(3))
+    elapsed = blocks[1]
     elapsed = max_over_ranks(elapsed, device)
     fwd_b, bwd_b = algo_bytes(s.t["u"].shape[0])
     return {"value": aggregate_throughput((fwd_b + bwd_b) * steps, world, elapsed) / 1e9, "unit": "GB/s", "h2d_bytes_per_step": h2d,
             "d2h_bytes_per_step": d2h_box[0], "steps": steps, "ms_per_step": elapsed / steps * 1e3,
+            "ms_per_step_blocks": [b / steps * 1e3 for b in blocks],
             "api": "mamba_ssm.ops.selective_scan_interface.selective_scan_fn + autograd backward",
             "pipeline": "h2d / kernels / d2h on three streams, two buffer sets: copies of step i+1 and i-1 overlap the kernels of step i"}
 
