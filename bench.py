@@ -13,7 +13,7 @@ A "step" = one forward + one backward of the fused selective scan over `clips` c
   e2e       the same op through the public API (mamba_ssm.ops.selective_scan_interface.
             selective_scan_fn + autograd backward) with HOST (pinned) inputs copied in and all
             results copied out inside the timed region.
-  roofline  the dominant kernel (scan_bwd_main_kernel) timed alone with CUDA events.
+  roofline  the dominant kernel (seg_bwd_kernel) timed alone with CUDA events.
   cpu_baseline / --impl reference   the torch port of selective_scan_ref (oracle/torch_port.py)
             timed on the host cores over a bounded sample of the same workload.
 
@@ -343,14 +343,14 @@ def run_ours(args, rank, world, local_rank):
     traffic = None
     try:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
-            traffic = json.load(f).get("scan_bwd_main_kernel_bytes_per_launch")
+            traffic = json.load(f).get("seg_bwd_kernel_bytes_per_launch")
     except Exception:
         pass
-    roofline = {"bound": "hbm", "kernel": "scan_bwd_main_kernel", "achieved": bwd_b / t_main / 1e9, "peak": peak,
+    roofline = {"bound": "hbm", "kernel": "seg_bwd_kernel", "achieved": bwd_b / t_main / 1e9, "peak": peak,
                 "unit": "GB/s", "frac": bwd_b / t_main / 1e9 / peak, "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": bwd_b, "us_per_launch": t_main * 1e6,
-                "note": "N=16 states per (channel, token): ~25 issue slots and 2 MUFU per state-step make this "
-                        "kernel instruction-issue bound, not HBM bound, on B200 (DESIGN.md section 5)"}
+                "note": "N=16 states per (channel, token): ~26 issue slots, 1 MUFU and 6.6 shared-memory/shuffle wavefront "
+                        "bytes per state-step make this kernel issue / LSU bound, not HBM bound, on B200 (DESIGN.md section 5)"}
 
     # ---- conv1d fwd / bwd at the same shape (x = first half of xz), for the record
     conv = bench_conv(clips, device, torch)
