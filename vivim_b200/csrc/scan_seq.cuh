@@ -241,6 +241,10 @@ __global__ void __launch_bounds__(kSegThreads, 9) seg_agg_kernel(const vv_scan_a
     }
     const int S = gridDim.x;
     float2* out = reinterpret_cast<float2*>(a.agg) + (((int64_t)c.b * a.dim + d) * S + c.seg) * N;
+    // Launched as a programmatic dependent: everything above only reads this call's inputs and may overlap the
+    // tail of the preceding kernel; `agg` may still be read by it (a carry pass of an earlier call), so the
+    // stores wait for its completion.
+    pdl_wait();
 #pragma unroll
     for (int k = 0; k < NQ; ++k) {
         const int n = q * NQ + k;
@@ -353,20 +357,25 @@ __global__ void __launch_bounds__(kSegThreads) seg_fwd_kernel(const vv_scan_args
     stB.load(reinterpret_cast<const T*>(a.Bm) + c.b * a.B_bs + c.g * a.B_gs, a.B_ns, N, c.t0, L);
     stC.load(reinterpret_cast<const T*>(a.Cm) + c.b * a.C_bs + c.g * a.C_gs, a.C_ns, N, c.t0, L);
     float A2[NQ], h[NQ];
-    pdl_wait();   // chk comes from the carry kernel; everything above overlaps its tail
+#pragma unroll
+    for (int k = 0; k < NQ; ++k) {
+        const int n = q * NQ + k;
+        A2[k] = n < N ? a.A[d * a.A_ds + n * a.A_ns] * kLog2e : 0.f;
+    }
+    pdl_trigger();   // a dependent launch (the reverse aggregate of a backward that follows directly) may start its loads
+    stB.store(t_B);
+    stC.store(t_C);
+    pre.finish(a.z != nullptr, f_dt + r * kF32Pitch, f_dr + r * kF32Pitch, t_u + r * SegTile<T>::kPitch,
+               t_z + r * SegTile<T>::kPitch, q, L, bias, sp);
+    pdl_wait();   // chk comes from the carry kernel; the loads, the softplus pre-pass and the tile fills above overlap it
     {
         const float* E = a.chk + (((int64_t)c.b * a.dim + d) * S + c.seg) * N;
 #pragma unroll
         for (int k = 0; k < NQ; ++k) {
             const int n = q * NQ + k;
-            A2[k] = n < N ? a.A[d * a.A_ds + n * a.A_ns] * kLog2e : 0.f;
             h[k] = n < N ? E[n] : 0.f;
         }
     }
-    stB.store(t_B);
-    stC.store(t_C);
-    pre.finish(a.z != nullptr, f_dt + r * kF32Pitch, f_dr + r * kF32Pitch, t_u + r * SegTile<T>::kPitch,
-               t_z + r * SegTile<T>::kPitch, q, L, bias, sp);
     __syncthreads();
     {
         // the raw u / z rows receive the gated / pre-gate output in place: positions {2q, 2q+1} of a

@@ -191,7 +191,7 @@ int launch_seg_agg(const vv_scan_args& a, const SegPlan& p, cudaStream_t st) {
     const size_t smem = 2 * (size_t)vv::kSegRows * vv::kF32Pitch + (size_t)vv::kSeg * NB * sizeof(float);
     int rc;
     if ((rc = set_smem(vv::seg_agg_kernel<T, kVec, NB, kRev>, smem)) != VV_OK) return rc;
-    launch_kernel(vv::seg_agg_kernel<T, kVec, NB, kRev>, p.grid, dim3(vv::kSegThreads), smem, st, false, a);
+    launch_kernel(vv::seg_agg_kernel<T, kVec, NB, kRev>, p.grid, dim3(vv::kSegThreads), smem, st, use_pdl(), a);
     return check_launch(kRev ? "seg_agg_kernel<rev>" : "seg_agg_kernel<fwd>");
 }
 
