@@ -49,9 +49,20 @@ class ScanArgs(Structure):
     ]
 
 
+class DwConv3dArgs(Structure):
+    """vv_dwconv3d_args"""
+    _fields_ = [
+        ("x", c_void_p), ("weight", c_void_p), ("bias", c_void_p), ("out", c_void_p),
+        ("dout", c_void_p), ("dx", c_void_p), ("dweight", c_void_p), ("dbias", c_void_p),
+        ("batch", c_int32), ("frames", c_int32), ("height", c_int32), ("width", c_int32), ("channels", c_int32),
+        ("io_dtype", c_int32),
+    ]
+
+
 # every symbol include/vivim_b200.h declares (checked by tests/test_cabi.py)
 EXPORTS = ("vv_version", "vv_last_error", "vv_scan_num_segments", "vv_conv1d_fwd", "vv_conv1d_bwd",
-           "vv_scan_fwd", "vv_scan_bwd", "vv_last_launch_count", "vv_scan_set_pass_mask")
+           "vv_scan_fwd", "vv_scan_bwd", "vv_last_launch_count", "vv_scan_set_pass_mask",
+           "vv_dwconv3d_fwd", "vv_dwconv3d_bwd")
 
 _lib = None
 
@@ -72,7 +83,8 @@ def lib() -> ctypes.CDLL:
         L.vv_scan_num_segments.argtypes = [c_int]
         L.vv_scan_num_segments.restype = c_int
         for name, argt in (("vv_conv1d_fwd", ConvArgs), ("vv_conv1d_bwd", ConvArgs),
-                           ("vv_scan_fwd", ScanArgs), ("vv_scan_bwd", ScanArgs)):
+                           ("vv_scan_fwd", ScanArgs), ("vv_scan_bwd", ScanArgs),
+                           ("vv_dwconv3d_fwd", DwConv3dArgs), ("vv_dwconv3d_bwd", DwConv3dArgs)):
             fn = getattr(L, name)
             fn.argtypes = [POINTER(argt), c_void_p]
             fn.restype = c_int

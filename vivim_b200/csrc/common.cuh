@@ -226,6 +226,24 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
+// two packed 16-bit elements -> fp32 pair
+template <typename T> __device__ __forceinline__ float2 unpack_pair(uint32_t w);
+template <> __device__ __forceinline__ float2 unpack_pair<__nv_bfloat16>(uint32_t w) {
+    return make_float2(__uint_as_float(w << 16), __uint_as_float(w & 0xffff0000u));
+}
+template <> __device__ __forceinline__ float2 unpack_pair<__half>(uint32_t w) {
+    return __half22float2(*reinterpret_cast<const __half2*>(&w));
+}
+// a pair of adjacent elements (4-byte aligned for 16-bit T, 8-byte for fp32)
+template <typename T> __device__ __forceinline__ float2 load_pair(const T* p);
+template <> __device__ __forceinline__ float2 load_pair<float>(const float* p) { return *reinterpret_cast<const float2*>(p); }
+template <> __device__ __forceinline__ float2 load_pair<__nv_bfloat16>(const __nv_bfloat16* p) {
+    return unpack_pair<__nv_bfloat16>(*reinterpret_cast<const uint32_t*>(p));
+}
+template <> __device__ __forceinline__ float2 load_pair<__half>(const __half* p) {
+    return unpack_pair<__half>(*reinterpret_cast<const uint32_t*>(p));
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -5,9 +5,11 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <algorithm>
 
 #include "../../include/vivim_b200.h"
 #include "conv1d.cuh"
+#include "dwconv3d.cuh"
 #include "scan_bwd.cuh"
 #include "scan_seq.cuh"
 
@@ -89,6 +91,68 @@ int launch_conv(const vv_conv1d_args* a, void* stream) {
         case VV_F32: return launch_conv_t<float, kBwd>(*a, vec, st);
         case VV_F16: return launch_conv_t<__half, kBwd>(*a, vec, st);
         default: return launch_conv_t<__nv_bfloat16, kBwd>(*a, vec, st);
+    }
+}
+
+// ---------------------------------------------------------------- depthwise conv3d dispatch
+template <typename T, bool kBwd>
+int launch_dw_t(const vv_dwconv3d_args& a, cudaStream_t st) {
+    const vv::DwGeom g{a.batch, a.frames, a.height, a.width, a.channels};
+    const bool vec = a.channels % 8 == 0 && vec_ok(kBwd ? a.dout : a.x, 1, {}) && vec_ok(kBwd ? a.dx : a.out, 1, {}) &&
+                     !env_int("VV_FORCE_SCALAR_IO", 0);
+    const int cvecs = (a.channels + 7) / 8, xt = (a.width + vv::kDwX - 1) / vv::kDwX;
+    const int64_t total = (int64_t)a.batch * a.frames * a.height * xt * cvecs;
+    const unsigned blocks = (unsigned)((total + vv::kDwThreads - 1) / vv::kDwThreads);
+    int rc = VV_OK;
+    if (!kBwd) {
+        if (vec) vv::dwconv3d_kernel<T, true, false><<<blocks, vv::kDwThreads, 0, st>>>(
+            reinterpret_cast<const T*>(a.x), a.weight, a.bias, reinterpret_cast<T*>(a.out), g);
+        else vv::dwconv3d_kernel<T, false, false><<<blocks, vv::kDwThreads, 0, st>>>(
+            reinterpret_cast<const T*>(a.x), a.weight, a.bias, reinterpret_cast<T*>(a.out), g);
+        return check_launch("dwconv3d_kernel<fwd>");
+    }
+    if (a.dx) {
+        if (vec) vv::dwconv3d_kernel<T, true, true><<<blocks, vv::kDwThreads, 0, st>>>(
+            reinterpret_cast<const T*>(a.dout), a.weight, nullptr, reinterpret_cast<T*>(a.dx), g);
+        else vv::dwconv3d_kernel<T, false, true><<<blocks, vv::kDwThreads, 0, st>>>(
+            reinterpret_cast<const T*>(a.dout), a.weight, nullptr, reinterpret_cast<T*>(a.dx), g);
+        if ((rc = check_launch("dwconv3d_kernel<dgrad>")) != VV_OK) return rc;
+    }
+    if (a.dweight) {
+        const int64_t npos = (int64_t)a.batch * a.frames * a.height * a.width;
+        const unsigned gx = (unsigned)((a.channels + 63) / 64);
+        int64_t gy = (4 * 148 + gx - 1) / gx;                       // ~4 CTAs per SM over the whole grid
+        gy = std::max<int64_t>(1, std::min<int64_t>(gy, (npos + vv::kDwSlots - 1) / vv::kDwSlots));
+        vv::dwconv3d_wgrad_kernel<T><<<dim3(gx, (unsigned)gy), dim3(32, vv::kDwSlots), 0, st>>>(
+            reinterpret_cast<const T*>(a.x), reinterpret_cast<const T*>(a.dout), a.dweight, a.dbias, g);
+        if ((rc = check_launch("dwconv3d_wgrad_kernel")) != VV_OK) return rc;
+    }
+    return VV_OK;
+}
+
+template <bool kBwd>
+int launch_dw(const vv_dwconv3d_args* a, void* stream) {
+    g_launches = 0;
+    if (!a) return fail(VV_ERR_BAD_ARG, "dwconv3d: null args");
+    if (!a->weight) return fail(VV_ERR_BAD_ARG, "dwconv3d: weight is required");
+    if (!kBwd && (!a->x || !a->out)) return fail(VV_ERR_BAD_ARG, "dwconv3d_fwd: x and out are required");
+    if (kBwd && !a->dout) return fail(VV_ERR_BAD_ARG, "dwconv3d_bwd: dout is required");
+    if (kBwd && a->dweight && !a->x) return fail(VV_ERR_BAD_ARG, "dwconv3d_bwd: x is required for the weight gradient");
+    if (kBwd && a->dbias && !a->dweight) return fail(VV_ERR_BAD_ARG, "dwconv3d_bwd: dbias needs dweight");
+    if (a->batch <= 0 || a->frames <= 0 || a->height <= 0 || a->width <= 0 || a->channels <= 0)
+        return fail(VV_ERR_BAD_ARG, "dwconv3d: sizes must be positive");
+    if (!valid_dtype(a->io_dtype)) return fail(VV_ERR_BAD_ARG, "dwconv3d: dtype must be fp32, fp16 or bf16");
+    const int es = elem_size(a->io_dtype);
+    if (!elem_aligned(a->x, es) || !elem_aligned(a->out, es) || !elem_aligned(a->dout, es) || !elem_aligned(a->dx, es))
+        return fail(VV_ERR_ALIGN, "dwconv3d: tensor not aligned to its element size");
+    if (es == 2 && (a->channels % 2 != 0 || reinterpret_cast<uintptr_t>(a->x) % 4 != 0 || reinterpret_cast<uintptr_t>(a->dout) % 4 != 0) &&
+        kBwd && a->dweight)
+        return fail(VV_ERR_UNSUPPORTED, "dwconv3d_bwd: 16-bit weight gradient needs an even channel count and 4-byte aligned tensors");
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    switch (a->io_dtype) {
+        case VV_F32: return launch_dw_t<float, kBwd>(*a, st);
+        case VV_F16: return launch_dw_t<__half, kBwd>(*a, st);
+        default: return launch_dw_t<__nv_bfloat16, kBwd>(*a, st);
     }
 }
 
@@ -300,6 +364,8 @@ int vv_scan_num_segments(int seqlen) { return seqlen <= 0 ? 0 : (seqlen + VV_SCA
 
 int vv_conv1d_fwd(const vv_conv1d_args* a, void* stream) { return launch_conv<false>(a, stream); }
 int vv_conv1d_bwd(const vv_conv1d_args* a, void* stream) { return launch_conv<true>(a, stream); }
+int vv_dwconv3d_fwd(const vv_dwconv3d_args* a, void* stream) { return launch_dw<false>(a, stream); }
+int vv_dwconv3d_bwd(const vv_dwconv3d_args* a, void* stream) { return launch_dw<true>(a, stream); }
 int vv_scan_fwd(const vv_scan_args* a, void* stream) { return launch_scan<false>(a, stream); }
 int vv_scan_bwd(const vv_scan_args* a, void* stream) { return launch_scan<true>(a, stream); }
 

@@ -39,12 +39,19 @@ class Mamba(nn.Module):
         self.activation = "silu"
         self.act = nn.SiLU()
 
+        # Module creation / init calls in the reference's order (mamba_simple.py:68-186), so that the same
+        # torch seed gives the same parameters as the reference constructor.
         self.in_proj = nn.Linear(d_model, 2 * self.d_inner, bias=bias, **kw)
-        for sfx in _DIRECTIONS[bimamba_type]:
+        for i, sfx in enumerate(_DIRECTIONS[bimamba_type]):
             self._make_direction(sfx, conv_bias, device, kw)
+            if i == 0:
+                self._init_dt(dt_init, dt_scale, dt_min, dt_max, dt_init_floor, kw)
 
-        # only the first direction gets the variance-preserving dt init (mamba_simple.py:88-108);
-        # dt_proj_b / dt_proj_s keep nn.Linear's default init in the reference fork
+        self.out_proj = nn.Linear(self.d_inner, d_model, bias=bias, **kw)
+
+    def _init_dt(self, dt_init, dt_scale, dt_min, dt_max, dt_init_floor, kw):
+        """Only the first direction gets the variance-preserving dt init (mamba_simple.py:88-108); dt_proj_b /
+        dt_proj_s keep nn.Linear's default init in the reference fork."""
         std = self.dt_rank ** -0.5 * dt_scale
         if dt_init == "constant":
             nn.init.constant_(self.dt_proj.weight, std)
@@ -57,8 +64,6 @@ class Mamba(nn.Module):
         with torch.no_grad():
             self.dt_proj.bias.copy_(dt + torch.log(-torch.expm1(-dt)))   # softplus^-1(dt)
         self.dt_proj.bias._no_reinit = True
-
-        self.out_proj = nn.Linear(self.d_inner, d_model, bias=bias, **kw)
 
     def _make_direction(self, sfx, conv_bias, device, kw):
         """Parameters of one scan direction: A{sfx}_log, D{sfx}, conv1d{sfx}, x_proj{sfx}, dt_proj{sfx}."""
