@@ -125,17 +125,17 @@ int vv_scan_bwd(const vv_scan_args *a, void *stream);
  * Replaces what the reference's DWConv module (modeling/vivim.py:57-68: tokens -> transpose -> nn.Conv3d(C, C, 3, 1, 1,
  * groups=C) -> flatten -> transpose) asks of cuDNN, directly on the token layout: x, out, dout, dx are
  * (B, frames, H, W, C) contiguous, channels innermost (= the (B, N, C) token tensor, N = frames*H*W).
- *   out[b,t,y,x,c] = bias[c] + sum_{dt,dy,dx in 0..2} weight[c, (dt*3+dy)*3+dx] * in[b, t+dt-1, y+dy-1, x+dx-1, c]
- * weight is the Conv3d parameter (C,1,3,3,3) viewed as float32 (C,27); zero padding.
+ *   out[b,t,y,x,c] = bias[c] + sum_{dt,dy,dx in 0..2} weight[(dt*3+dy)*3+dx, c] * in[b, t+dt-1, y+dy-1, x+dx-1, c]
+ * weight is the Conv3d parameter (C,1,3,3,3) as float32, TAP-MAJOR: (27,C) = param.view(C,27).t(); zero padding.
  */
 typedef struct {
     const void *x;        /* (B,T,H,W,C) io_dtype */
-    const float *weight;  /* (C,27) float32 */
+    const float *weight;  /* (27,C) float32, tap-major */
     const float *bias;    /* (C) float32 or NULL */
     void *out;            /* fwd: (B,T,H,W,C) io_dtype */
     const void *dout;     /* bwd: (B,T,H,W,C) io_dtype */
     void *dx;             /* bwd: (B,T,H,W,C) io_dtype, or NULL to skip the input gradient */
-    float *dweight;       /* bwd: (C,27) float32 +=, or NULL to skip the parameter gradients */
+    float *dweight;       /* bwd: (27,C) float32 +=, or NULL to skip the parameter gradients */
     float *dbias;         /* bwd: (C) float32 +=, or NULL */
     int32_t batch, frames, height, width, channels;
     int32_t io_dtype;     /* VV_F32 / VV_F16 / VV_BF16 */

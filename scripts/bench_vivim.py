@@ -28,6 +28,8 @@ ap.add_argument("--steps", type=int, default=20)
 ap.add_argument("--warmup", type=int, default=5)
 ap.add_argument("--image", type=int, default=256)
 ap.add_argument("--graph", action="store_true")
+ap.add_argument("--bucket-mb", type=int, default=25)
+ap.add_argument("--bf16-allreduce", action="store_true")
 args = ap.parse_args()
 rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
 local = int(os.environ.get("LOCAL_RANK", 0))
@@ -61,7 +63,15 @@ if args.graph:
 
 if args.mode == "train":
     model.train()
-    net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local]) if world > 1 else model
+    net = model
+    if world > 1:
+        # gradients live directly in the all-reduce buckets (no copy), and travel as bf16 (the DDP all-reduce is the
+        # only collective of this workload: north_star)
+        from torch.distributed.algorithms.ddp_comm_hooks import default_hooks
+        net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local], gradient_as_bucket_view=True,
+                                                        bucket_cap_mb=args.bucket_mb)
+        if args.bf16_allreduce:
+            net.register_comm_hook(None, default_hooks.bf16_compress_hook)
     opt = torch.optim.AdamW([p for p in model.parameters() if p.requires_grad], lr=1e-4, weight_decay=1e-2)
 
     def step():

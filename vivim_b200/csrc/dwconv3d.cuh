@@ -52,7 +52,8 @@ __device__ __forceinline__ void dw_load(const T* __restrict__ base, const DwGeom
 }
 
 // kMirror = false: forward (taps as stored, + bias).  kMirror = true: input gradient (taps mirrored, no bias).
-// weight: fp32 (C, 27), tap = (dt * 3 + dy) * 3 + dx.
+// weight: fp32 (27, C) -- tap-major, so that the 8 channels of a thread are 32 contiguous bytes and a warp reads
+// 1 KB contiguous per tap; tap = (dt * 3 + dy) * 3 + dx.
 template <typename T, bool kVec, bool kMirror>
 __global__ void __launch_bounds__(kDwThreads) dwconv3d_kernel(const T* __restrict__ in, const float* __restrict__ weight,
                                                               const float* __restrict__ bias, T* __restrict__ out,
@@ -79,19 +80,35 @@ __global__ void __launch_bounds__(kDwThreads) dwconv3d_kernel(const T* __restric
 #pragma unroll 1
     for (int row = 0; row < 9; ++row) {
         const int dt = row / 3, dy = row - dt * 3;
-        float win[kDwX + 2][8];
+        const int ts = t + dt - 1, ys = y + dy - 1;
+        const bool row_ok = (unsigned)ts < (unsigned)g.T && (unsigned)ys < (unsigned)g.H;
+        // the window stays packed in the I/O dtype (4 registers per 8 bf16 channels) and is widened at each use:
+        // 80 registers, 3 CTAs per SM -- the kernel is latency bound, more warps in flight matter more than ALU ops
+        Raw8<T, kVec> win[kDwX + 2];
+        const T* rowp = in + (((int64_t)b * g.T + ts) * g.H + ys) * g.W * g.C + c0;
 #pragma unroll
-        for (int j = 0; j < kDwX + 2; ++j) dw_load<T, kVec>(in, g, b, t + dt - 1, y + dy - 1, x0 + j - 1, c0, win[j]);
+        for (int j = 0; j < kDwX + 2; ++j) {
+            const int xs = x0 + j - 1;
+            if (kVec) win[j].load(rowp + (int64_t)xs * g.C, (row_ok && (unsigned)xs < (unsigned)g.W) ? 0 : 1, 1);
+            else win[j].load(rowp + (int64_t)xs * g.C, (row_ok && (unsigned)xs < (unsigned)g.W) ? 0 : 8, min(8, g.C - c0));
+        }
 #pragma unroll
         for (int dx = 0; dx < 3; ++dx) {
             const int tap = kMirror ? 26 - (row * 3 + dx) : row * 3 + dx;
             float w[8];
+            if (kVec) {
+                load8_vec<float>(weight + (int64_t)tap * g.C + c0, w);
+            } else {
 #pragma unroll
-            for (int i = 0; i < 8; ++i) w[i] = (c0 + i < g.C) ? __ldg(weight + (int64_t)(c0 + i) * 27 + tap) : 0.f;
+                for (int i = 0; i < 8; ++i) w[i] = (c0 + i < g.C) ? __ldg(weight + (int64_t)tap * g.C + c0 + i) : 0.f;
+            }
 #pragma unroll
-            for (int j = 0; j < kDwX; ++j)
+            for (int j = 0; j < kDwX; ++j) {
+                float v[8];
+                win[j + dx].unpack(v);
 #pragma unroll
-                for (int i = 0; i < 8; ++i) acc[j][i] = fmaf(w[i], win[j + dx][i], acc[j][i]);
+                for (int i = 0; i < 8; ++i) acc[j][i] = fmaf(w[i], v[i], acc[j][i]);
+            }
         }
     }
 #pragma unroll
@@ -110,72 +127,112 @@ __global__ void __launch_bounds__(kDwThreads) dwconv3d_kernel(const T* __restric
     }
 }
 
-// weight / bias gradient.  grid (ceil(C / 64), position blocks); block (32 lanes = 64 channels, 8 position slots).
-constexpr int kDwSlots = 8;
+// weight / bias gradient.  A thread owns 4 channels (64-bit accesses; a warp = 128 contiguous channels) and the 9
+// taps of ONE frame offset dt; it walks rows of kDwX outputs with the same sliding window as the forward kernel
+// (3 rows x (kDwX + 2) loads of x + kDwX loads of dout for 36 x kDwX FMAs), striding over the (b, frame, y, x-block)
+// rows.  block (32 lanes, 3 frame offsets, kDwSlots row slots); grid (ceil(C / 128), row blocks).  The row slots of
+// a CTA are reduced in shared memory, then one fp32 atomicAdd per (CTA, channel, tap).
+constexpr int kDwSlots = 4;
 
 template <typename T>
-__device__ __forceinline__ float2 dw_load2(const T* __restrict__ p, int c, int C) {
-    if (sizeof(T) == 4 || c + 1 >= C)   // fp32: the pair need not be 8-byte aligned when C is odd
-        return make_float2(c < C ? to_f32<T>(p[0]) : 0.f, c + 1 < C ? to_f32<T>(p[1]) : 0.f);
-    return load_pair<T>(p);
+__device__ __forceinline__ void dw_load4(const T* __restrict__ p, int c, int C, bool vec, float (&v)[4]) {
+    if (vec) {
+        if (sizeof(T) == 4) {
+            const float4 x = __ldg(reinterpret_cast<const float4*>(p));
+            v[0] = x.x; v[1] = x.y; v[2] = x.z; v[3] = x.w;
+        } else {
+            const uint2 x = __ldg(reinterpret_cast<const uint2*>(p));
+            const float2 lo = unpack_pair<T>(x.x), hi = unpack_pair<T>(x.y);
+            v[0] = lo.x; v[1] = lo.y; v[2] = hi.x; v[3] = hi.y;
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) v[i] = (c + i < C) ? to_f32<T>(p[i]) : 0.f;
+    }
 }
 
 template <typename T>
-__global__ void __launch_bounds__(32 * kDwSlots) dwconv3d_wgrad_kernel(const T* __restrict__ x, const T* __restrict__ dout,
-                                                                       float* __restrict__ dweight, float* __restrict__ dbias,
-                                                                       const DwGeom g) {
-    __shared__ float2 red[kDwSlots][32];
-    const int lane = threadIdx.x, slot = threadIdx.y;
-    const int c = (blockIdx.x * 32 + lane) * 2;
+__global__ void __launch_bounds__(32 * 3 * kDwSlots) dwconv3d_wgrad_kernel(const T* __restrict__ x, const T* __restrict__ dout,
+                                                                           float* __restrict__ dweight, float* __restrict__ dbias,
+                                                                           const DwGeom g, const int vec) {
+    __shared__ float4 red[kDwSlots][3][32];
+    const int lane = threadIdx.x, dt = threadIdx.y, slot = threadIdx.z;
+    const int c = (blockIdx.x * 32 + lane) * 4;
     const bool live = c < g.C;
-    const int64_t npos = (int64_t)g.B * g.T * g.H * g.W;
-    float2 acc[27], accb = make_float2(0.f, 0.f);
+    const int xt = (g.W + kDwX - 1) / kDwX;
+    const int64_t nrows = (int64_t)g.B * g.T * g.H * xt;
+    float acc[9][4], accb[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-    for (int k = 0; k < 27; ++k) acc[k] = make_float2(0.f, 0.f);
+    for (int k = 0; k < 9; ++k)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) acc[k][i] = 0.f;
     if (live) {
-        for (int64_t p = (int64_t)blockIdx.y * kDwSlots + slot; p < npos; p += (int64_t)gridDim.y * kDwSlots) {
-            int64_t r = p;
-            const int xx = (int)(r % g.W); r /= g.W;
+        for (int64_t rix = (int64_t)blockIdx.y * kDwSlots + slot; rix < nrows; rix += (int64_t)gridDim.y * kDwSlots) {
+            int64_t r = rix;
+            const int xb = (int)(r % xt); r /= xt;
             const int y = (int)(r % g.H); r /= g.H;
             const int t = (int)(r % g.T);
-            const float2 go = dw_load2<T>(dout + p * g.C + c, c, g.C);
-            accb.x += go.x;
-            accb.y += go.y;
+            const int b = (int)(r / g.T);
+            const int x0 = xb * kDwX, ts = t + dt - 1;
+            if ((unsigned)ts >= (unsigned)g.T) continue;       // this frame offset falls outside the clip: zero padding
+            float go[kDwX][4];
 #pragma unroll
-            for (int dt = 0; dt < 3; ++dt)
+            for (int j = 0; j < kDwX; ++j) {
+                if (x0 + j < g.W) {
+                    dw_load4<T>(dout + ((((int64_t)b * g.T + t) * g.H + y) * g.W + x0 + j) * g.C + c, c, g.C, vec, go[j]);
+                } else {
 #pragma unroll
-                for (int dy = 0; dy < 3; ++dy)
+                    for (int i = 0; i < 4; ++i) go[j][i] = 0.f;
+                }
+                if (dt == 1) {
 #pragma unroll
-                    for (int dx = 0; dx < 3; ++dx) {
-                        const int tt = t + dt - 1, yy = y + dy - 1, xq = xx + dx - 1;
-                        if ((unsigned)tt < (unsigned)g.T && (unsigned)yy < (unsigned)g.H && (unsigned)xq < (unsigned)g.W) {
-                            const int64_t q = p + ((int64_t)(dt - 1) * g.H + (dy - 1)) * g.W + (dx - 1);
-                            const float2 xv = dw_load2<T>(x + q * g.C + c, c, g.C);
-                            const int k = (dt * 3 + dy) * 3 + dx;
-                            acc[k].x = fmaf(go.x, xv.x, acc[k].x);
-                            acc[k].y = fmaf(go.y, xv.y, acc[k].y);
-                        }
+                    for (int i = 0; i < 4; ++i) accb[i] += go[j][i];
+                }
+            }
+#pragma unroll
+            for (int dy = 0; dy < 3; ++dy) {
+                const int ys = y + dy - 1;
+                if ((unsigned)ys >= (unsigned)g.H) continue;
+                float win[kDwX + 2][4];
+#pragma unroll
+                for (int j = 0; j < kDwX + 2; ++j) {
+                    const int xs = x0 + j - 1;
+                    if ((unsigned)xs < (unsigned)g.W) {
+                        dw_load4<T>(x + ((((int64_t)b * g.T + ts) * g.H + ys) * g.W + xs) * g.C + c, c, g.C, vec, win[j]);
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) win[j][i] = 0.f;
                     }
+                }
+#pragma unroll
+                for (int dx = 0; dx < 3; ++dx)
+#pragma unroll
+                    for (int j = 0; j < kDwX; ++j)
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) acc[dy * 3 + dx][i] = fmaf(go[j][i], win[j + dx][i], acc[dy * 3 + dx][i]);
+            }
         }
     }
-    // reduce the position slots of the CTA, one tap at a time (fully unrolled: acc[] stays in registers)
+    // reduce the row slots of the CTA, one tap at a time (fully unrolled: acc[] stays in registers)
 #pragma unroll
-    for (int k = 0; k < 28; ++k) {
-        red[slot][lane] = k < 27 ? acc[k < 27 ? k : 0] : accb;
+    for (int k = 0; k < 10; ++k) {
+        const float* src = k < 9 ? acc[k < 9 ? k : 0] : accb;
+        red[slot][dt][lane] = make_float4(src[0], src[1], src[2], src[3]);
         __syncthreads();
-        if (slot == 0 && live) {
-            float2 s = red[0][lane];
+        if (slot == 0 && live && (k < 9 || (dt == 1 && dbias))) {
+            float4 s = red[0][dt][lane];
 #pragma unroll
             for (int j = 1; j < kDwSlots; ++j) {
-                s.x += red[j][lane].x;
-                s.y += red[j][lane].y;
+                const float4 o = red[j][dt][lane];
+                s.x += o.x; s.y += o.y; s.z += o.z; s.w += o.w;
             }
-            if (k < 27) {
-                atomicAdd(dweight + (int64_t)c * 27 + k, s.x);
-                if (c + 1 < g.C) atomicAdd(dweight + (int64_t)(c + 1) * 27 + k, s.y);
-            } else if (dbias) {
-                atomicAdd(dbias + c, s.x);
-                if (c + 1 < g.C) atomicAdd(dbias + c + 1, s.y);
+            const float sv[4] = {s.x, s.y, s.z, s.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                if (c + i < g.C) {
+                    if (k < 9) atomicAdd(dweight + (int64_t)(dt * 9 + k) * g.C + c + i, sv[i]);
+                    else atomicAdd(dbias + c + i, sv[i]);
+                }
             }
         }
         __syncthreads();

@@ -119,12 +119,15 @@ int launch_dw_t(const vv_dwconv3d_args& a, cudaStream_t st) {
         if ((rc = check_launch("dwconv3d_kernel<dgrad>")) != VV_OK) return rc;
     }
     if (a.dweight) {
-        const int64_t npos = (int64_t)a.batch * a.frames * a.height * a.width;
-        const unsigned gx = (unsigned)((a.channels + 63) / 64);
-        int64_t gy = (4 * 148 + gx - 1) / gx;                       // ~4 CTAs per SM over the whole grid
-        gy = std::max<int64_t>(1, std::min<int64_t>(gy, (npos + vv::kDwSlots - 1) / vv::kDwSlots));
-        vv::dwconv3d_wgrad_kernel<T><<<dim3(gx, (unsigned)gy), dim3(32, vv::kDwSlots), 0, st>>>(
-            reinterpret_cast<const T*>(a.x), reinterpret_cast<const T*>(a.dout), a.dweight, a.dbias, g);
+        const int64_t nrows = (int64_t)a.batch * a.frames * a.height * xt;
+        const unsigned gx = (unsigned)((a.channels + 127) / 128);
+        int64_t gy = (3 * 148 + gx - 1) / gx;                       // ~3 CTAs of 384 threads per SM over the whole grid
+        gy = std::max<int64_t>(1, std::min<int64_t>(gy, (nrows + vv::kDwSlots - 1) / vv::kDwSlots));
+        const int es2 = elem_size(a.io_dtype);
+        const int vec4 = a.channels % 4 == 0 && reinterpret_cast<uintptr_t>(a.x) % (4 * es2) == 0 &&
+                         reinterpret_cast<uintptr_t>(a.dout) % (4 * es2) == 0 && !env_int("VV_FORCE_SCALAR_IO", 0);
+        vv::dwconv3d_wgrad_kernel<T><<<dim3(gx, (unsigned)gy), dim3(32, 3, vv::kDwSlots), 0, st>>>(
+            reinterpret_cast<const T*>(a.x), reinterpret_cast<const T*>(a.dout), a.dweight, a.dbias, g, vec4);
         if ((rc = check_launch("dwconv3d_wgrad_kernel")) != VV_OK) return rc;
     }
     return VV_OK;
@@ -145,9 +148,6 @@ int launch_dw(const vv_dwconv3d_args* a, void* stream) {
     const int es = elem_size(a->io_dtype);
     if (!elem_aligned(a->x, es) || !elem_aligned(a->out, es) || !elem_aligned(a->dout, es) || !elem_aligned(a->dx, es))
         return fail(VV_ERR_ALIGN, "dwconv3d: tensor not aligned to its element size");
-    if (es == 2 && (a->channels % 2 != 0 || reinterpret_cast<uintptr_t>(a->x) % 4 != 0 || reinterpret_cast<uintptr_t>(a->dout) % 4 != 0) &&
-        kBwd && a->dweight)
-        return fail(VV_ERR_UNSUPPORTED, "dwconv3d_bwd: 16-bit weight gradient needs an even channel count and 4-byte aligned tensors");
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     switch (a->io_dtype) {
         case VV_F32: return launch_dw_t<float, kBwd>(*a, st);

@@ -55,7 +55,7 @@ class _DwConv3dTokens(torch.autograd.Function):
         global LAUNCHES
         _check_inputs(tokens, weight, bias, frames, height, width)
         x = tokens.contiguous()
-        w27 = weight.detach().float().reshape(weight.shape[0], 27).contiguous()
+        w27 = weight.detach().float().reshape(weight.shape[0], 27).t().contiguous()     # tap-major (27, C)
         b32 = bias.detach().float().contiguous() if bias is not None else None
         out = torch.empty_like(x)
         if x.numel():
@@ -79,7 +79,7 @@ class _DwConv3dTokens(torch.autograd.Function):
         dx = torch.empty_like(x) if need_x else None
         # accumulated in fp32 zeros, cast back to the parameter dtype (the convention of the scan / conv1d shims)
         dw = torch.zeros(w27.shape, dtype=torch.float32, device=x.device) if (need_w or need_b) else None
-        db = torch.zeros(w27.shape[0], dtype=torch.float32, device=x.device) if need_b else None
+        db = torch.zeros(w27.shape[1], dtype=torch.float32, device=x.device) if need_b else None
         if x.numel() and (need_x or need_w or need_b):
             a = _args(x, w27, None, frames, height, width)
             a.x, a.dout = x.data_ptr(), dout.data_ptr()
@@ -89,7 +89,7 @@ class _DwConv3dTokens(torch.autograd.Function):
             _call("vv_dwconv3d_bwd", a, x.device)
             LAUNCHES += (1 if need_x else 0) + (1 if dw is not None else 0)
         wd, bd = ctx.param_dtypes
-        return (dx, dw.reshape(-1, 1, 3, 3, 3).to(wd) if need_w else None, db.to(bd) if need_b else None,
+        return (dx, dw.t().reshape(-1, 1, 3, 3, 3).to(wd) if need_w else None, db.to(bd) if need_b else None,
                 None, None, None)
 
 
