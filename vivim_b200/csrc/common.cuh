@@ -226,6 +226,11 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
+// packed fp32 pairs (FFMA2 / FMUL2 / FADD2 of sm_100): one issue slot for two lanes of fp32 math
+__device__ __forceinline__ float2 mul2(float2 x, float2 y) { return __fmul2_rn(x, y); }
+__device__ __forceinline__ float2 add2(float2 x, float2 y) { return __fadd2_rn(x, y); }
+__device__ __forceinline__ float2 fma2(float2 x, float2 y, float2 z) { return __ffma2_rn(x, y, z); }
+
 // two packed 16-bit elements -> fp32 pair
 template <typename T> __device__ __forceinline__ float2 unpack_pair(uint32_t w);
 template <> __device__ __forceinline__ float2 unpack_pair<__nv_bfloat16>(uint32_t w) {

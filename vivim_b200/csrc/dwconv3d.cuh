@@ -5,20 +5,25 @@
 // transpose.  cuDNN serves the depthwise 3-D case with per-group convolveNd engines: in a Vivim training step
 // (batch 3, 256x256, clip 5) its dgrad + wgrad kernels are 10752 launches and 90 % of the GPU time
 // (profiles/r01_vivim_step.md).  The op is a 27-tap stencil with no reuse across channels, i.e. bandwidth
-// bound: 2 tensors in/out forward, 3 + a (C, 27) reduction backward.
+// bound: 2 tensors in/out forward, 3 + a (27, C) reduction backward.
 //
 // Design (B200-first): work directly on the TOKEN layout (B, nf, H, W, C), channels innermost, so neither
-// transpose exists.  One thread owns 8 channels (one 128-bit access) of kDwX consecutive x positions of one
-// (b, frame, y) row and slides a 3-wide window along x: 9 rows x (kDwX + 2) vector loads for kDwX outputs; a
-// warp covers 256 contiguous channels (512 B per request).  Neighbouring rows / frames are re-read through
-// L1 / L2 (the whole activation is < 32 MB, L2 is 126 MB).  The weights of the thread's 8 channels are read
-// through the read-only path (27 x 32 B per thread, L1 resident).
-//   forward   out = bias + sum_tap w[c, tap] x[p + off(tap)]
-//   backward  dx  = sum_tap w[c, tap] dout[p - off(tap)]          (same kernel, mirrored taps, no bias)
-//             dw[c, tap] = sum_p dout[p] x[p + off(tap)],  db[c] = sum_p dout[p]
-//   the weight gradient keeps 27 x 2 fp32 accumulators per thread (2 channels, 32-bit accesses, a warp = 64
-//   contiguous channels), strides over the positions, reduces the 8 position slots of a CTA in shared memory
-//   and issues one fp32 atomicAdd per (CTA, channel, tap).
+// transpose exists, and keep everything that is reused in REGISTERS -- shared memory and L1 hits go through the
+// same 128 B/clk data pipe, which is what bounded the first version (27 window + 27 weight reads per output
+// through L1: 69 % data-pipe utilisation at 13 % of the HBM roofline).  One thread owns 2 channels (a warp = 64
+// contiguous channels = one 128-byte line per position) of a column of kDwX x-positions of one (b, y) row and
+// walks the frames:
+//   * its 27 x 2 weights live in registers for the whole walk;
+//   * of every input frame it loads 3 rows x (kDwX + 2) positions ONCE and scatters them into the rolling
+//     accumulators of the three output frames they touch (f-1, f, f+1); a finished frame is stored and its
+//     accumulators recycled.  That is (kDwX + 2) * 3 / kDwX = 4.5 reads per output instead of 27, no weight traffic,
+//     and the multiply-adds are packed fp32 pairs (FFMA2).
+//   forward   out = bias + sum_tap w[tap, c] x[p + off(tap)]
+//   backward  dx  = sum_tap w[tap, c] dout[p - off(tap)]          (same kernel, taps mirrored when loaded, no bias)
+//             dw[tap, c] = sum_p dout[p] x[p + off(tap)],  db[c] = sum_p dout[p]
+//   the weight gradient is the same walk with the roles swapped: 27 x 2 accumulators in registers, dout of frames
+//   f-1, f, f+1 rolling in registers; the columns a CTA covers are reduced in shared memory, then one fp32
+//   atomicAdd per (CTA, channel, tap).
 #pragma once
 
 #include "../../include/vivim_b200.h"
@@ -26,214 +31,237 @@
 
 namespace vv {
 
-constexpr int kDwX = 4;            // x positions per thread (sliding window)
+constexpr int kDwX = 4;            // x positions per thread
 constexpr int kDwThreads = 256;
+constexpr int kDwCols = 8;         // columns per CTA of the weight-gradient kernel (block = 32 lanes x kDwCols)
 
 struct DwGeom {
     int B, T, H, W, C;
 };
 
-// 8 channels of one position (zeros outside the volume)
-template <typename T, bool kVec>
-__device__ __forceinline__ void dw_load(const T* __restrict__ base, const DwGeom& g, int b, int t, int y, int x, int c0,
-                                        float (&v)[8]) {
-    if ((unsigned)t < (unsigned)g.T && (unsigned)y < (unsigned)g.H && (unsigned)x < (unsigned)g.W) {
-        const T* p = base + ((((int64_t)b * g.T + t) * g.H + y) * g.W + x) * g.C + c0;
-        if (kVec) {
-            load8_vec<T>(p, v);
-        } else {
-#pragma unroll
-            for (int i = 0; i < 8; ++i) v[i] = (c0 + i < g.C) ? to_f32<T>(p[i]) : 0.f;
+// 2 adjacent channels of one position.  kPair: C is even and the tensor is aligned for one 4-byte (16-bit T) /
+// 8-byte (fp32) access; otherwise element-wise with a channel bound.
+template <typename T, bool kPair>
+__device__ __forceinline__ float2 dw_ld(const T* __restrict__ p, int c, int C) {
+    if (kPair) {
+        if (sizeof(T) == 4) {
+            const float2 v = __ldg(reinterpret_cast<const float2*>(p));
+            return v;
+        }
+        return unpack_pair<T>(__ldg(reinterpret_cast<const uint32_t*>(p)));
+    }
+    return make_float2(to_f32<T>(p[0]), c + 1 < C ? to_f32<T>(p[1]) : 0.f);
+}
+template <typename T, bool kPair>
+__device__ __forceinline__ void dw_st(T* __restrict__ p, int c, int C, float2 v) {
+    if (kPair) {
+        if (sizeof(T) == 4) {
+            *reinterpret_cast<float2*>(p) = v;
+        } else if (sizeof(T) == 2) {
+            T tmp[2] = {from_f32<T>(v.x), from_f32<T>(v.y)};
+            *reinterpret_cast<uint32_t*>(p) = *reinterpret_cast<const uint32_t*>(tmp);
         }
     } else {
+        p[0] = from_f32<T>(v.x);
+        if (c + 1 < C) p[1] = from_f32<T>(v.y);
+    }
+}
+__device__ __forceinline__ float2 dw_ldw(const float* __restrict__ p, int c, int C, bool pair) {
+    if (pair) return __ldg(reinterpret_cast<const float2*>(p));
+    return make_float2(__ldg(p), c + 1 < C ? __ldg(p + 1) : 0.f);
+}
+
+struct DwCoord {
+    int b, y, x0, c;
+    bool live;
+};
+// thread index -> (channel pair fastest, x block, y, batch)
+__device__ __forceinline__ DwCoord dw_coord(const DwGeom& g, int64_t idx) {
+    const int cp = (g.C + 1) / 2, xt = (g.W + kDwX - 1) / kDwX;
+    DwCoord k;
+    k.live = idx < (int64_t)g.B * g.H * xt * cp;
+    k.c = (int)(idx % cp) * 2;
+    int64_t r = idx / cp;
+    k.x0 = (int)(r % xt) * kDwX; r /= xt;
+    k.y = (int)(r % g.H);
+    k.b = (int)(r / g.H);
+    return k;
+}
+
+// A pair of channels as loaded (one 32-bit register for 16-bit T): all 3 x (kDwX + 2) reads of a frame are issued
+// before the first use, so that a thread has 72 bytes in flight -- the kernel is bound by memory-level parallelism.
+template <typename T, bool kPair> struct DwRaw {
+    float2 v;
+    __device__ __forceinline__ void load(const T* __restrict__ p, int c, int C, bool ok) {
+        v = ok ? dw_ld<T, kPair>(p, c, C) : make_float2(0.f, 0.f);
+    }
+    __device__ __forceinline__ float2 get() const { return v; }
+};
+template <> struct DwRaw<__nv_bfloat16, true> {
+    uint32_t r;
+    __device__ __forceinline__ void load(const __nv_bfloat16* __restrict__ p, int, int, bool ok) {
+        r = ok ? __ldg(reinterpret_cast<const uint32_t*>(p)) : 0u;
+    }
+    __device__ __forceinline__ float2 get() const { return unpack_pair<__nv_bfloat16>(r); }
+};
+template <> struct DwRaw<__half, true> {
+    uint32_t r;
+    __device__ __forceinline__ void load(const __half* __restrict__ p, int, int, bool ok) {
+        r = ok ? __ldg(reinterpret_cast<const uint32_t*>(p)) : 0u;
+    }
+    __device__ __forceinline__ float2 get() const { return unpack_pair<__half>(r); }
+};
+
+// the 3 rows (y-1, y, y+1) of frame fs of the column's window: positions x0-1 .. x0+kDwX, zeros outside the volume
+template <typename T, bool kPair>
+__device__ __forceinline__ void dw_frame(const T* __restrict__ in, const DwGeom& g, const DwCoord& k, int fs,
+                                         DwRaw<T, kPair> (&win)[3][kDwX + 2]) {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) v[i] = 0.f;
+    for (int dy = 0; dy < 3; ++dy) {
+        const int ys = k.y + dy - 1;
+        const bool ok = (unsigned)ys < (unsigned)g.H;
+        const T* row = in + ((((int64_t)k.b * g.T + fs) * g.H + (ok ? ys : 0)) * g.W) * g.C + k.c;
+#pragma unroll
+        for (int j = 0; j < kDwX + 2; ++j) {
+            const int xs = k.x0 + j - 1;
+            win[dy][j].load(row + (int64_t)xs * g.C, k.c, g.C, ok && (unsigned)xs < (unsigned)g.W);
+        }
     }
 }
 
-// kMirror = false: forward (taps as stored, + bias).  kMirror = true: input gradient (taps mirrored, no bias).
-// weight: fp32 (27, C) -- tap-major, so that the 8 channels of a thread are 32 contiguous bytes and a warp reads
-// 1 KB contiguous per tap; tap = (dt * 3 + dy) * 3 + dx.
-template <typename T, bool kVec, bool kMirror>
+// kMirror = false: forward (+ bias).  kMirror = true: input gradient (weights mirrored, no bias).
+// weight: fp32 (27, C), tap-major; tap = (dt * 3 + dy) * 3 + dx.
+template <typename T, bool kPair, bool kMirror>
 __global__ void __launch_bounds__(kDwThreads) dwconv3d_kernel(const T* __restrict__ in, const float* __restrict__ weight,
                                                               const float* __restrict__ bias, T* __restrict__ out,
                                                               const DwGeom g) {
-    const int cvecs = (g.C + 7) / 8;
-    const int xt = (g.W + kDwX - 1) / kDwX;
-    const int64_t total = (int64_t)g.B * g.T * g.H * xt * cvecs;
-    const int64_t idx = (int64_t)blockIdx.x * kDwThreads + threadIdx.x;
-    if (idx >= total) return;
-    const int cv = (int)(idx % cvecs);
-    int64_t r = idx / cvecs;
-    const int xb = (int)(r % xt); r /= xt;
-    const int y = (int)(r % g.H); r /= g.H;
-    const int t = (int)(r % g.T);
-    const int b = (int)(r / g.T);
-    const int c0 = cv * 8, x0 = xb * kDwX;
+    const DwCoord k = dw_coord(g, (int64_t)blockIdx.x * kDwThreads + threadIdx.x);
+    if (!k.live) return;
+    const bool wpair = g.C % 2 == 0;
+    float2 w[27];
+#pragma unroll
+    for (int t = 0; t < 27; ++t) w[t] = dw_ldw(weight + (int64_t)(kMirror ? 26 - t : t) * g.C + k.c, k.c, g.C, wpair);
+    const float2 b2 = (!kMirror && bias) ? dw_ldw(bias + k.c, k.c, g.C, wpair) : make_float2(0.f, 0.f);
 
-    float acc[kDwX][8];
+    // a0: output frame f-1, a1: frame f, a2: frame f+1 while input frame f is being scattered
+    float2 a0[kDwX], a1[kDwX], a2[kDwX];
 #pragma unroll
-    for (int j = 0; j < kDwX; ++j)
-#pragma unroll
-        for (int i = 0; i < 8; ++i) acc[j][i] = (!kMirror && bias && c0 + i < g.C) ? __ldg(bias + c0 + i) : 0.f;
+    for (int j = 0; j < kDwX; ++j) a0[j] = a1[j] = a2[j] = b2;
 
 #pragma unroll 1
-    for (int row = 0; row < 9; ++row) {
-        const int dt = row / 3, dy = row - dt * 3;
-        const int ts = t + dt - 1, ys = y + dy - 1;
-        const bool row_ok = (unsigned)ts < (unsigned)g.T && (unsigned)ys < (unsigned)g.H;
-        // the window stays packed in the I/O dtype (4 registers per 8 bf16 channels) and is widened at each use:
-        // 80 registers, 3 CTAs per SM -- the kernel is latency bound, more warps in flight matter more than ALU ops
-        Raw8<T, kVec> win[kDwX + 2];
-        const T* rowp = in + (((int64_t)b * g.T + ts) * g.H + ys) * g.W * g.C + c0;
+    for (int f = 0; f < g.T; ++f) {
+        DwRaw<T, kPair> raw[3][kDwX + 2];
+        dw_frame<T, kPair>(in, g, k, f, raw);
 #pragma unroll
-        for (int j = 0; j < kDwX + 2; ++j) {
-            const int xs = x0 + j - 1;
-            if (kVec) win[j].load(rowp + (int64_t)xs * g.C, (row_ok && (unsigned)xs < (unsigned)g.W) ? 0 : 1, 1);
-            else win[j].load(rowp + (int64_t)xs * g.C, (row_ok && (unsigned)xs < (unsigned)g.W) ? 0 : 8, min(8, g.C - c0));
-        }
+        for (int dy = 0; dy < 3; ++dy) {
+            float2 win[kDwX + 2];
 #pragma unroll
-        for (int dx = 0; dx < 3; ++dx) {
-            const int tap = kMirror ? 26 - (row * 3 + dx) : row * 3 + dx;
-            float w[8];
-            if (kVec) {
-                load8_vec<float>(weight + (int64_t)tap * g.C + c0, w);
-            } else {
+            for (int j = 0; j < kDwX + 2; ++j) win[j] = raw[dy][j].get();
 #pragma unroll
-                for (int i = 0; i < 8; ++i) w[i] = (c0 + i < g.C) ? __ldg(weight + (int64_t)tap * g.C + c0 + i) : 0.f;
-            }
+            for (int dx = 0; dx < 3; ++dx) {
+                const float2 w_prev = w[(2 * 3 + dy) * 3 + dx], w_cur = w[(1 * 3 + dy) * 3 + dx], w_next = w[(0 * 3 + dy) * 3 + dx];
 #pragma unroll
-            for (int j = 0; j < kDwX; ++j) {
-                float v[8];
-                win[j + dx].unpack(v);
-#pragma unroll
-                for (int i = 0; i < 8; ++i) acc[j][i] = fmaf(w[i], v[i], acc[j][i]);
+                for (int j = 0; j < kDwX; ++j) {
+                    a0[j] = fma2(w_prev, win[j + dx], a0[j]);   // input frame f is frame t+1 of output t = f-1: dt = 2
+                    a1[j] = fma2(w_cur, win[j + dx], a1[j]);
+                    a2[j] = fma2(w_next, win[j + dx], a2[j]);
+                }
             }
         }
-    }
+        if (f > 0) {
+            T* row = out + ((((int64_t)k.b * g.T + f - 1) * g.H + k.y) * g.W) * g.C + k.c;
 #pragma unroll
-    for (int j = 0; j < kDwX; ++j) {
-        const int x = x0 + j;
-        if (x < g.W) {
-            T* p = out + ((((int64_t)b * g.T + t) * g.H + y) * g.W + x) * g.C + c0;
-            if (kVec) {
-                store8_vec<T>(p, acc[j]);
-            } else {
+            for (int j = 0; j < kDwX; ++j)
+                if (k.x0 + j < g.W) dw_st<T, kPair>(row + (int64_t)(k.x0 + j) * g.C, k.c, g.C, a0[j]);
+        }
 #pragma unroll
-                for (int i = 0; i < 8; ++i)
-                    if (c0 + i < g.C) p[i] = from_f32<T>(acc[j][i]);
-            }
+        for (int j = 0; j < kDwX; ++j) {
+            a0[j] = a1[j];
+            a1[j] = a2[j];
+            a2[j] = b2;
         }
     }
+    T* row = out + ((((int64_t)k.b * g.T + g.T - 1) * g.H + k.y) * g.W) * g.C + k.c;
+#pragma unroll
+    for (int j = 0; j < kDwX; ++j)
+        if (k.x0 + j < g.W) dw_st<T, kPair>(row + (int64_t)(k.x0 + j) * g.C, k.c, g.C, a0[j]);
 }
 
-// weight / bias gradient.  A thread owns 4 channels (64-bit accesses; a warp = 128 contiguous channels) and the 9
-// taps of ONE frame offset dt; it walks rows of kDwX outputs with the same sliding window as the forward kernel
-// (3 rows x (kDwX + 2) loads of x + kDwX loads of dout for 36 x kDwX FMAs), striding over the (b, frame, y, x-block)
-// rows.  block (32 lanes, 3 frame offsets, kDwSlots row slots); grid (ceil(C / 128), row blocks).  The row slots of
-// a CTA are reduced in shared memory, then one fp32 atomicAdd per (CTA, channel, tap).
-constexpr int kDwSlots = 4;
-
-template <typename T>
-__device__ __forceinline__ void dw_load4(const T* __restrict__ p, int c, int C, bool vec, float (&v)[4]) {
-    if (vec) {
-        if (sizeof(T) == 4) {
-            const float4 x = __ldg(reinterpret_cast<const float4*>(p));
-            v[0] = x.x; v[1] = x.y; v[2] = x.z; v[3] = x.w;
-        } else {
-            const uint2 x = __ldg(reinterpret_cast<const uint2*>(p));
-            const float2 lo = unpack_pair<T>(x.x), hi = unpack_pair<T>(x.y);
-            v[0] = lo.x; v[1] = lo.y; v[2] = hi.x; v[3] = hi.y;
-        }
-    } else {
-#pragma unroll
-        for (int i = 0; i < 4; ++i) v[i] = (c + i < C) ? to_f32<T>(p[i]) : 0.f;
-    }
-}
-
-template <typename T>
-__global__ void __launch_bounds__(32 * 3 * kDwSlots) dwconv3d_wgrad_kernel(const T* __restrict__ x, const T* __restrict__ dout,
-                                                                           float* __restrict__ dweight, float* __restrict__ dbias,
-                                                                           const DwGeom g, const int vec) {
-    __shared__ float4 red[kDwSlots][3][32];
-    const int lane = threadIdx.x, dt = threadIdx.y, slot = threadIdx.z;
-    const int c = (blockIdx.x * 32 + lane) * 4;
-    const bool live = c < g.C;
+// weight / bias gradient: block (32 lanes = 64 channels, kDwCols columns), grid (ceil(C / 64), column blocks)
+template <typename T, bool kPair>
+__global__ void __launch_bounds__(32 * kDwCols) dwconv3d_wgrad_kernel(const T* __restrict__ x, const T* __restrict__ dout,
+                                                                      float* __restrict__ dweight, float* __restrict__ dbias,
+                                                                      const DwGeom g) {
+    __shared__ float2 red[kDwCols][32];
+    const int lane = threadIdx.x, col = threadIdx.y;
     const int xt = (g.W + kDwX - 1) / kDwX;
-    const int64_t nrows = (int64_t)g.B * g.T * g.H * xt;
-    float acc[9][4], accb[4] = {0.f, 0.f, 0.f, 0.f};
+    const int64_t ncols = (int64_t)g.B * g.H * xt;
+    DwCoord k;
+    k.c = (blockIdx.x * 32 + lane) * 2;
+    k.live = k.c < g.C;
+    float2 acc[27], accb = make_float2(0.f, 0.f);
 #pragma unroll
-    for (int k = 0; k < 9; ++k)
+    for (int t = 0; t < 27; ++t) acc[t] = make_float2(0.f, 0.f);
+    if (k.live) {
+        for (int64_t ci = (int64_t)blockIdx.y * kDwCols + col; ci < ncols; ci += (int64_t)gridDim.y * kDwCols) {
+            int64_t r = ci;
+            k.x0 = (int)(r % xt) * kDwX; r /= xt;
+            k.y = (int)(r % g.H);
+            k.b = (int)(r / g.H);
+            // dout of the column for frames f-1, f, f+1 (zeros outside the clip)
+            float2 g0[kDwX], g1[kDwX], g2[kDwX];
+            auto load_g = [&](int f, float2 (&dst)[kDwX]) {
+                const T* row = dout + ((((int64_t)k.b * g.T + (f < g.T ? f : 0)) * g.H + k.y) * g.W) * g.C + k.c;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) acc[k][i] = 0.f;
-    if (live) {
-        for (int64_t rix = (int64_t)blockIdx.y * kDwSlots + slot; rix < nrows; rix += (int64_t)gridDim.y * kDwSlots) {
-            int64_t r = rix;
-            const int xb = (int)(r % xt); r /= xt;
-            const int y = (int)(r % g.H); r /= g.H;
-            const int t = (int)(r % g.T);
-            const int b = (int)(r / g.T);
-            const int x0 = xb * kDwX, ts = t + dt - 1;
-            if ((unsigned)ts >= (unsigned)g.T) continue;       // this frame offset falls outside the clip: zero padding
-            float go[kDwX][4];
+                for (int j = 0; j < kDwX; ++j)
+                    dst[j] = (f < g.T && k.x0 + j < g.W) ? dw_ld<T, kPair>(row + (int64_t)(k.x0 + j) * g.C, k.c, g.C)
+                                                         : make_float2(0.f, 0.f);
+            };
 #pragma unroll
-            for (int j = 0; j < kDwX; ++j) {
-                if (x0 + j < g.W) {
-                    dw_load4<T>(dout + ((((int64_t)b * g.T + t) * g.H + y) * g.W + x0 + j) * g.C + c, c, g.C, vec, go[j]);
-                } else {
+            for (int j = 0; j < kDwX; ++j) g0[j] = make_float2(0.f, 0.f);
+            load_g(0, g1);
+#pragma unroll 1
+            for (int f = 0; f < g.T; ++f) {
+                DwRaw<T, kPair> raw[3][kDwX + 2];
+                dw_frame<T, kPair>(x, g, k, f, raw);
+                load_g(f + 1, g2);
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) go[j][i] = 0.f;
+                for (int j = 0; j < kDwX; ++j) accb = add2(accb, g1[j]);
+#pragma unroll
+                for (int dy = 0; dy < 3; ++dy) {
+                    float2 win[kDwX + 2];
+#pragma unroll
+                    for (int j = 0; j < kDwX + 2; ++j) win[j] = raw[dy][j].get();
+#pragma unroll
+                    for (int dx = 0; dx < 3; ++dx)
+#pragma unroll
+                        for (int j = 0; j < kDwX; ++j) {
+                            // x frame f is frame t + dt - 1 of output t: t = f+1 (dt 0), f (dt 1), f-1 (dt 2)
+                            acc[(0 * 3 + dy) * 3 + dx] = fma2(g2[j], win[j + dx], acc[(0 * 3 + dy) * 3 + dx]);
+                            acc[(1 * 3 + dy) * 3 + dx] = fma2(g1[j], win[j + dx], acc[(1 * 3 + dy) * 3 + dx]);
+                            acc[(2 * 3 + dy) * 3 + dx] = fma2(g0[j], win[j + dx], acc[(2 * 3 + dy) * 3 + dx]);
+                        }
                 }
-                if (dt == 1) {
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) accb[i] += go[j][i];
+                for (int j = 0; j < kDwX; ++j) {
+                    g0[j] = g1[j];
+                    g1[j] = g2[j];
                 }
-            }
-#pragma unroll
-            for (int dy = 0; dy < 3; ++dy) {
-                const int ys = y + dy - 1;
-                if ((unsigned)ys >= (unsigned)g.H) continue;
-                float win[kDwX + 2][4];
-#pragma unroll
-                for (int j = 0; j < kDwX + 2; ++j) {
-                    const int xs = x0 + j - 1;
-                    if ((unsigned)xs < (unsigned)g.W) {
-                        dw_load4<T>(x + ((((int64_t)b * g.T + ts) * g.H + ys) * g.W + xs) * g.C + c, c, g.C, vec, win[j]);
-                    } else {
-#pragma unroll
-                        for (int i = 0; i < 4; ++i) win[j][i] = 0.f;
-                    }
-                }
-#pragma unroll
-                for (int dx = 0; dx < 3; ++dx)
-#pragma unroll
-                    for (int j = 0; j < kDwX; ++j)
-#pragma unroll
-                        for (int i = 0; i < 4; ++i) acc[dy * 3 + dx][i] = fmaf(go[j][i], win[j + dx][i], acc[dy * 3 + dx][i]);
             }
         }
     }
-    // reduce the row slots of the CTA, one tap at a time (fully unrolled: acc[] stays in registers)
+    // reduce the columns of the CTA, one tap at a time (fully unrolled: acc[] stays in registers)
 #pragma unroll
-    for (int k = 0; k < 10; ++k) {
-        const float* src = k < 9 ? acc[k < 9 ? k : 0] : accb;
-        red[slot][dt][lane] = make_float4(src[0], src[1], src[2], src[3]);
+    for (int t = 0; t < 28; ++t) {
+        red[col][lane] = t < 27 ? acc[t < 27 ? t : 0] : accb;
         __syncthreads();
-        if (slot == 0 && live && (k < 9 || (dt == 1 && dbias))) {
-            float4 s = red[0][dt][lane];
+        if (col == 0 && k.live && (t < 27 || dbias)) {
+            float2 s = red[0][lane];
 #pragma unroll
-            for (int j = 1; j < kDwSlots; ++j) {
-                const float4 o = red[j][dt][lane];
-                s.x += o.x; s.y += o.y; s.z += o.z; s.w += o.w;
-            }
-            const float sv[4] = {s.x, s.y, s.z, s.w};
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                if (c + i < g.C) {
-                    if (k < 9) atomicAdd(dweight + (int64_t)(dt * 9 + k) * g.C + c + i, sv[i]);
-                    else atomicAdd(dbias + c + i, sv[i]);
-                }
-            }
+            for (int j = 1; j < kDwCols; ++j) s = add2(s, red[j][lane]);
+            float* dst = t < 27 ? dweight + (int64_t)t * g.C + k.c : dbias + k.c;
+            atomicAdd(dst, s.x);
+            if (k.c + 1 < g.C) atomicAdd(dst + 1, s.y);
         }
         __syncthreads();
     }

@@ -53,10 +53,6 @@ __host__ __device__ constexpr size_t bwd_smem_bytes(int NB) {
     return 16 * (size_t)(2 * NB * kBwdSlots + kBwdWarps * bwd_warp_f4(NB));
 }
 
-// packed fp32 pairs (FFMA2 / FMUL2 / FADD2 of sm_100): one issue slot for two lanes of math
-__device__ __forceinline__ float2 mul2(float2 x, float2 y) { return __fmul2_rn(x, y); }
-__device__ __forceinline__ float2 add2(float2 x, float2 y) { return __fadd2_rn(x, y); }
-__device__ __forceinline__ float2 fma2(float2 x, float2 y, float2 z) { return __ffma2_rn(x, y, z); }
 __device__ __forceinline__ void acc4(float4& v, float2 lo, float2 hi) {
     asm("add.rn.ftz.f32x2 %0, %0, %1;" : "+l"(*reinterpret_cast<unsigned long long*>(&v.x)) : "l"(*reinterpret_cast<const unsigned long long*>(&lo)));
     asm("add.rn.ftz.f32x2 %0, %0, %1;" : "+l"(*reinterpret_cast<unsigned long long*>(&v.z)) : "l"(*reinterpret_cast<const unsigned long long*>(&hi)));

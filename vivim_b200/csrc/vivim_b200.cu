@@ -98,36 +98,39 @@ int launch_conv(const vv_conv1d_args* a, void* stream) {
 template <typename T, bool kBwd>
 int launch_dw_t(const vv_dwconv3d_args& a, cudaStream_t st) {
     const vv::DwGeom g{a.batch, a.frames, a.height, a.width, a.channels};
-    const bool vec = a.channels % 8 == 0 && vec_ok(kBwd ? a.dout : a.x, 1, {}) && vec_ok(kBwd ? a.dx : a.out, 1, {}) &&
-                     !env_int("VV_FORCE_SCALAR_IO", 0);
-    const int cvecs = (a.channels + 7) / 8, xt = (a.width + vv::kDwX - 1) / vv::kDwX;
-    const int64_t total = (int64_t)a.batch * a.frames * a.height * xt * cvecs;
-    const unsigned blocks = (unsigned)((total + vv::kDwThreads - 1) / vv::kDwThreads);
+    const size_t pair_bytes = 2 * sizeof(T);
+    auto aligned = [&](const void* p) { return p == nullptr || reinterpret_cast<uintptr_t>(p) % pair_bytes == 0; };
+    const bool pair = a.channels % 2 == 0 && aligned(a.x) && aligned(a.out) && aligned(a.dout) && aligned(a.dx) &&
+                      reinterpret_cast<uintptr_t>(a.weight) % 8 == 0 && !env_int("VV_FORCE_SCALAR_IO", 0);
+    const int cp = (a.channels + 1) / 2, xt = (a.width + vv::kDwX - 1) / vv::kDwX;
+    const int64_t ncols = (int64_t)a.batch * a.height * xt;
+    const unsigned blocks = (unsigned)((ncols * cp + vv::kDwThreads - 1) / vv::kDwThreads);
     int rc = VV_OK;
+#define VV_DW_STENCIL(MIRROR, IN, BIAS, OUT)                                                                          \
+    do {                                                                                                              \
+        if (pair) vv::dwconv3d_kernel<T, true, MIRROR><<<blocks, vv::kDwThreads, 0, st>>>(                            \
+            reinterpret_cast<const T*>(IN), a.weight, BIAS, reinterpret_cast<T*>(OUT), g);                            \
+        else vv::dwconv3d_kernel<T, false, MIRROR><<<blocks, vv::kDwThreads, 0, st>>>(                                \
+            reinterpret_cast<const T*>(IN), a.weight, BIAS, reinterpret_cast<T*>(OUT), g);                            \
+    } while (0)
     if (!kBwd) {
-        if (vec) vv::dwconv3d_kernel<T, true, false><<<blocks, vv::kDwThreads, 0, st>>>(
-            reinterpret_cast<const T*>(a.x), a.weight, a.bias, reinterpret_cast<T*>(a.out), g);
-        else vv::dwconv3d_kernel<T, false, false><<<blocks, vv::kDwThreads, 0, st>>>(
-            reinterpret_cast<const T*>(a.x), a.weight, a.bias, reinterpret_cast<T*>(a.out), g);
+        VV_DW_STENCIL(false, a.x, a.bias, a.out);
         return check_launch("dwconv3d_kernel<fwd>");
     }
     if (a.dx) {
-        if (vec) vv::dwconv3d_kernel<T, true, true><<<blocks, vv::kDwThreads, 0, st>>>(
-            reinterpret_cast<const T*>(a.dout), a.weight, nullptr, reinterpret_cast<T*>(a.dx), g);
-        else vv::dwconv3d_kernel<T, false, true><<<blocks, vv::kDwThreads, 0, st>>>(
-            reinterpret_cast<const T*>(a.dout), a.weight, nullptr, reinterpret_cast<T*>(a.dx), g);
+        VV_DW_STENCIL(true, a.dout, nullptr, a.dx);
         if ((rc = check_launch("dwconv3d_kernel<dgrad>")) != VV_OK) return rc;
     }
+#undef VV_DW_STENCIL
     if (a.dweight) {
-        const int64_t nrows = (int64_t)a.batch * a.frames * a.height * xt;
-        const unsigned gx = (unsigned)((a.channels + 127) / 128);
-        int64_t gy = (3 * 148 + gx - 1) / gx;                       // ~3 CTAs of 384 threads per SM over the whole grid
-        gy = std::max<int64_t>(1, std::min<int64_t>(gy, (nrows + vv::kDwSlots - 1) / vv::kDwSlots));
-        const int es2 = elem_size(a.io_dtype);
-        const int vec4 = a.channels % 4 == 0 && reinterpret_cast<uintptr_t>(a.x) % (4 * es2) == 0 &&
-                         reinterpret_cast<uintptr_t>(a.dout) % (4 * es2) == 0 && !env_int("VV_FORCE_SCALAR_IO", 0);
-        vv::dwconv3d_wgrad_kernel<T><<<dim3(gx, (unsigned)gy), dim3(32, 3, vv::kDwSlots), 0, st>>>(
-            reinterpret_cast<const T*>(a.x), reinterpret_cast<const T*>(a.dout), a.dweight, a.dbias, g, vec4);
+        const unsigned gx = (unsigned)((a.channels + 63) / 64);
+        int64_t gy = (4 * 148 + gx - 1) / gx;                       // ~4 CTAs of 256 threads per SM over the whole grid
+        gy = std::max<int64_t>(1, std::min<int64_t>(gy, (ncols + vv::kDwCols - 1) / vv::kDwCols));
+        const dim3 grid(gx, (unsigned)gy), block(32, vv::kDwCols);
+        if (pair) vv::dwconv3d_wgrad_kernel<T, true><<<grid, block, 0, st>>>(
+            reinterpret_cast<const T*>(a.x), reinterpret_cast<const T*>(a.dout), a.dweight, a.dbias, g);
+        else vv::dwconv3d_wgrad_kernel<T, false><<<grid, block, 0, st>>>(
+            reinterpret_cast<const T*>(a.x), reinterpret_cast<const T*>(a.dout), a.dweight, a.dbias, g);
         if ((rc = check_launch("dwconv3d_wgrad_kernel")) != VV_OK) return rc;
     }
     return VV_OK;
