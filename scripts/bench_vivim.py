@@ -28,6 +28,9 @@ ap.add_argument("--steps", type=int, default=20)
 ap.add_argument("--warmup", type=int, default=5)
 ap.add_argument("--image", type=int, default=256)
 ap.add_argument("--graph", action="store_true")
+ap.add_argument("--full-graph", action="store_true",
+                help="training: capture forward + backward of the WHOLE network in one CUDA graph; gradients live in one "
+                     "flat buffer that is all-reduced (NCCL, average) with a single call, then a fused AdamW step")
 ap.add_argument("--bucket-mb", type=int, default=25)
 ap.add_argument("--bf16-allreduce", action="store_true")
 args = ap.parse_args()
@@ -61,7 +64,43 @@ if args.graph:
             seq[0] = graph_module(blk, (sample,), autocast_dtype=torch.bfloat16)
         size //= 2
 
-if args.mode == "train":
+if args.mode == "train" and args.full_graph:
+    model.train()
+    params = [p for p in model.parameters() if p.requires_grad]
+    flat = torch.zeros(sum(p.numel() for p in params), device=dev)       # every gradient is a view into this buffer
+    off = 0
+    for p in params:
+        p.grad = flat[off:off + p.numel()].view_as(p)
+        off += p.numel()
+    opt = torch.optim.AdamW(params, lr=1e-4, weight_decay=1e-2, fused=True, capturable=True)
+    loss_buf = torch.zeros((), device=dev)
+
+    def fwd_bwd():
+        flat.zero_()
+        with torch.autocast("cuda", dtype=torch.bfloat16, cache_enabled=False):
+            logits = model(clip)
+        loss = torch.nn.functional.cross_entropy(logits.float(), target)
+        loss.backward()
+        loss_buf.copy_(loss.detach())
+
+    side = torch.cuda.Stream(dev)
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        for _ in range(3):
+            fwd_bwd()
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        fwd_bwd()
+
+    def step():
+        graph.replay()
+        if world > 1:
+            dist.all_reduce(flat, op=dist.ReduceOp.AVG)
+        opt.step()
+        return loss_buf
+elif args.mode == "train":
     model.train()
     net = model
     if world > 1:
@@ -89,8 +128,10 @@ else:
         with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
             return model(clip).float().mean()
 
+first = None
 for _ in range(args.warmup):
     out = step()
+    first = float(out) if first is None else first
 if world > 1:
     dist.barrier()
 torch.cuda.synchronize()
@@ -111,7 +152,7 @@ if rank == 0:
                       "scaling": "weak", "dtype": "bf16", "data": "synthetic",
                       "config": {"workload": f"Vivim multiclass {args.mode}, image {args.image}, clip_length {frames}, "
                                              f"batch {batch} per GPU, 3 classes, random init",
-                                 "graphed_mamba_blocks": bool(args.graph)},
-                      "last_value": float(out)}), flush=True)
+                                 "graphed_mamba_blocks": bool(args.graph), "whole_step_graph": bool(args.full_graph)},
+                      "first_value": first, "last_value": float(out)}), flush=True)
 if world > 1:
     dist.destroy_process_group()
