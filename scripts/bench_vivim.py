@@ -65,41 +65,18 @@ if args.graph:
         size //= 2
 
 if args.mode == "train" and args.full_graph:
+    from vivim_b200.graphed import TrainStepGraph
     model.train()
-    params = [p for p in model.parameters() if p.requires_grad]
-    flat = torch.zeros(sum(p.numel() for p in params), device=dev)       # every gradient is a view into this buffer
-    off = 0
-    for p in params:
-        p.grad = flat[off:off + p.numel()].view_as(p)
-        off += p.numel()
-    opt = torch.optim.AdamW(params, lr=1e-4, weight_decay=1e-2, fused=True, capturable=True)
-    loss_buf = torch.zeros((), device=dev)
-
-    def fwd_bwd():
-        flat.zero_()
-        with torch.autocast("cuda", dtype=torch.bfloat16, cache_enabled=False):
-            logits = model(clip)
-        loss = torch.nn.functional.cross_entropy(logits.float(), target)
-        loss.backward()
-        loss_buf.copy_(loss.detach())
-
-    side = torch.cuda.Stream(dev)
-    side.wait_stream(torch.cuda.current_stream())
-    with torch.cuda.stream(side):
-        for _ in range(3):
-            fwd_bwd()
-    torch.cuda.current_stream().wait_stream(side)
-    torch.cuda.synchronize()
-    graph = torch.cuda.CUDAGraph()
-    with torch.cuda.graph(graph):
-        fwd_bwd()
+    tsg = TrainStepGraph(model, lambda logits, tgt: torch.nn.functional.cross_entropy(logits.float(), tgt),
+                         (clip,), (target,), autocast_dtype=torch.bfloat16)
+    opt = torch.optim.AdamW(tsg.params, lr=1e-4, weight_decay=1e-2, fused=True, capturable=True)
 
     def step():
-        graph.replay()
+        loss = tsg()
         if world > 1:
-            dist.all_reduce(flat, op=dist.ReduceOp.AVG)
+            dist.all_reduce(tsg.flat_grad, op=dist.ReduceOp.AVG)
         opt.step()
-        return loss_buf
+        return loss
 elif args.mode == "train":
     model.train()
     net = model

@@ -55,3 +55,31 @@ def test_vivim_training_step_runs(cuda_device):
     for name, p in model.named_parameters():
         if ".stages." in name:
             assert p.grad is not None and torch.isfinite(p.grad).all(), name
+
+
+@pytest.mark.gpu
+def test_whole_step_graph_matches_eager_gradients(cuda_device):
+    """vivim_b200.graphed.TrainStepGraph on one Temporal Mamba block (eval-free: no dropout inside): the flat
+    gradient buffer after a replay equals the eager gradients, and a second replay with a new batch tracks it."""
+    from vivim_b200.graphed import TrainStepGraph
+    from vivim_b200.temporal_model import TemporalMambaBlock
+    torch.manual_seed(0)
+    blk = TemporalMambaBlock(32).cuda().train()
+    loss_fn = lambda y, t: torch.nn.functional.mse_loss(y.float(), t)   # noqa: E731
+    xs = [torch.randn(2, 32, 5, 8, 8, device="cuda") for _ in range(2)]
+    ts = [torch.randn(2, 32, 5, 8, 8, device="cuda") for _ in range(2)]
+
+    def eager(x, t):
+        for p in blk.parameters():
+            p.grad = None
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            loss = loss_fn(blk(x), t)
+        loss.backward()
+        return float(loss), torch.cat([p.grad.flatten() for p in blk.parameters()]).clone()
+
+    want = [eager(x, t) for x, t in zip(xs, ts)]
+    step = TrainStepGraph(blk, loss_fn, (xs[0],), (ts[0],), autocast_dtype=torch.bfloat16)
+    for (x, t), (loss_ref, grad_ref) in zip(zip(xs, ts), want):
+        loss = float(step(x, t))
+        assert abs(loss - loss_ref) <= 1e-3 * abs(loss_ref)
+        assert rel_err(step.flat_grad.cpu().numpy(), grad_ref.cpu().numpy()) < 1e-2
