@@ -422,55 +422,81 @@ def bench_conv(clips, device, torch):
     return res
 
 
-def bench_e2e(s, steps, world, device, torch, dist):
-    """selective_scan_fn + backward through the public API: every step copies its inputs in from pinned
-    host memory and every result (out_z and all eight gradients) back out to pinned host memory.  The
-    copies of neighbouring steps overlap the kernels (three streams, two device-side buffer sets)."""
+def bench_e2e(s, steps, world, device, torch, dist, graphed=True):
+    """selective_scan_fn + backward through the public API: every step copies its inputs in from pinned host
+    memory and every result (out_z and all eight gradients) back out to pinned host memory.
+
+    Host side kept lean, because at 0.12 ms of kernels per step the Python / launch overhead is what a user
+    would otherwise measure: the inputs of a step are one flat pinned buffer (one H2D copy, the tensors are views
+    of the device copy), forward + backward are replayed as CUDA graphs (vivim_b200.graphed.graph_module around
+    selective_scan_fn -- the launches of this library are capture-safe), the nine results are gathered into one
+    flat device buffer (one D2H copy).  Copies of neighbouring steps overlap the kernels: three streams, two
+    buffer sets."""
     from mamba_ssm.ops.selective_scan_interface import selective_scan_fn
+    from vivim_b200.graphed import graph_module
     from vivim_b200.sharding import aggregate_throughput, max_over_ranks
-    pin = {k: v.pin_memory() for k, v in s.host.items()}
-    pin.update({k: v.cpu().pin_memory() for k, v in s.p.items()})
-    h2d = sum(v.numel() * v.element_size() for v in pin.values())
     order = ("u", "delta", "A", "B", "C", "D", "z", "bias")
+    src = dict(s.host)
+    src.update({k: v.cpu() for k, v in s.p.items()})
+    # flat layout: every tensor at a 256-byte aligned offset
+    offs, total = {}, 0
+    for k in order + ("dout",):
+        offs[k] = total
+        total += -(-src[k].numel() * src[k].element_size() // 256) * 256
+    pin_in = torch.empty(total, dtype=torch.uint8, pin_memory=True)
+
+    def views(flat):
+        return {k: flat[offs[k]:offs[k] + src[k].numel() * src[k].element_size()].view(src[k].dtype).view(src[k].shape)
+                for k in offs}
+
+    for k, v in views(pin_in).items():
+        v.copy_(src[k])
+    h2d = sum(v.numel() * v.element_size() for v in src.values())
     depth = 2
-    dev_in = [{k: torch.empty(v.shape, dtype=v.dtype, device=device) for k, v in pin.items()} for _ in range(depth)]
-    host_out = [None] * depth
+    dev_flat = [torch.empty(total, dtype=torch.uint8, device=device) for _ in range(depth)]
+    dev_in = [views(f) for f in dev_flat]
+
+    def scan(u, delta, A, B, C, D, z, bias):
+        return selective_scan_fn(u, delta, A, B, C, D, z=z, delta_bias=bias, delta_softplus=True)
+
+    fn = scan
+    if graphed:
+        sample = tuple(dev_in[0][n].clone().requires_grad_() for n in order)
+        fn = graph_module(scan, sample)
     s_in, s_cmp, s_out = (torch.cuda.Stream(device) for _ in range(3))
     ev_in = [torch.cuda.Event() for _ in range(depth)]
     ev_cmp = [torch.cuda.Event() for _ in range(depth)]
     ev_out = [torch.cuda.Event() for _ in range(depth)]
-    d2h_box = [0]
+    out_bytes = h2d - src["dout"].numel() * src["dout"].element_size() + src["u"].numel() * src["u"].element_size()
+    dev_out = [torch.empty(out_bytes, dtype=torch.uint8, device=device) for _ in range(depth)]
+    host_out = [torch.empty(out_bytes, dtype=torch.uint8, pin_memory=True) for _ in range(depth)]
 
     def one(i):
         k = i % depth
         with torch.cuda.stream(s_in):
             s_in.wait_event(ev_cmp[k])              # the kernels that last read this input set are done
-            for name, src in pin.items():
-                dev_in[k][name].copy_(src, non_blocking=True)
+            dev_flat[k].copy_(pin_in, non_blocking=True)
             ev_in[k].record(s_in)
         with torch.cuda.stream(s_cmp):
             s_cmp.wait_event(ev_in[k])
+            s_cmp.wait_event(ev_out[k])             # the previous results of this slot have left the device
             leaves = [dev_in[k][n].detach().requires_grad_() for n in order]
-            u, delta, A, B, C, D, z, bias = leaves
-            out = selective_scan_fn(u, delta, A, B, C, D, z=z, delta_bias=bias, delta_softplus=True)
+            out = fn(*leaves)
             out.backward(dev_in[k]["dout"])
             results = [out.detach()] + [x.grad for x in leaves]
+            torch.cat([r.reshape(-1).view(torch.uint8) for r in results], out=dev_out[k])
             ev_cmp[k].record(s_cmp)
         with torch.cuda.stream(s_out):
             s_out.wait_event(ev_cmp[k])
-            if host_out[k] is None:   # pinned result buffers, allocated once
-                host_out[k] = [torch.empty(r.shape, dtype=r.dtype, pin_memory=True) for r in results]
-            for h, r in zip(host_out[k], results):
-                r.record_stream(s_out)
-                h.copy_(r, non_blocking=True)
+            host_out[k].copy_(dev_out[k], non_blocking=True)
             ev_out[k].record(s_out)
-        d2h_box[0] = sum(r.numel() * r.element_size() for r in results)
 
     for i in range(2 * depth):
         one(i)
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
+
     def block():
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()                                 # current stream; the three streams start after it
@@ -487,17 +513,19 @@ def bench_e2e(s, steps, world, device, torch, dist):
         torch.cuda.synchronize()
         return e0.elapsed_time(e1) / 1e3
 
-    # three timed blocks of `steps` steps; the median block is reported (the host side of this path is
-    # Python + autograd, and a single block is at the mercy of one scheduling hiccup on the box)
+    # three timed blocks of `steps` steps; the median block is reported (a single block is at the mercy of one
+    # scheduling hiccup on the box)
     blocks = sorted(block() for _ in range(3))
     elapsed = blocks[1]
     elapsed = max_over_ranks(elapsed, device)
     fwd_b, bwd_b = algo_bytes(s.t["u"].shape[0])
     return {"value": aggregate_throughput((fwd_b + bwd_b) * steps, world, elapsed) / 1e9, "unit": "GB/s", "h2d_bytes_per_step": h2d,
-            "d2h_bytes_per_step": d2h_box[0], "steps": steps, "ms_per_step": elapsed / steps * 1e3,
+            "d2h_bytes_per_step": out_bytes, "steps": steps, "ms_per_step": elapsed / steps * 1e3,
             "ms_per_step_blocks": [b / steps * 1e3 for b in blocks],
-            "api": "mamba_ssm.ops.selective_scan_interface.selective_scan_fn + autograd backward",
-            "pipeline": "h2d / kernels / d2h on three streams, two buffer sets: copies of step i+1 and i-1 overlap the kernels of step i"}
+            "api": "mamba_ssm.ops.selective_scan_interface.selective_scan_fn + autograd backward"
+                   + (", replayed as CUDA graphs (vivim_b200.graphed.graph_module)" if graphed else ""),
+            "pipeline": "one flat H2D copy / kernels / one flat D2H copy on three streams, two buffer sets: copies of "
+                        "step i+1 and i-1 overlap the kernels of step i"}
 
 
 def main():
