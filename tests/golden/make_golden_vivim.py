@@ -79,6 +79,18 @@ def main():
             depths=np.array(DEPTHS), seed=np.array(SEED))
     print("logits", tuple(logits.shape), "params", sum(v.numel() for v in sd.values()))
 
+    # the reference's own DWConv module (modeling/vivim.py:57-68), forward + autograd gradients, on a tiny token tensor
+    torch.manual_seed(SEED + 2)
+    dw = ref_vivim.DWConv(dim=12)
+    nf, H, W = 3, 5, 6
+    x = torch.randn(2, nf * H * W, 12, requires_grad=True)
+    y = dw(x, nf, H, W)
+    go = torch.randn_like(y)
+    y.backward(go)
+    mg.save("vivim_dwconv", x=mg.npy(x), weight=mg.npy(dw.dwconv.weight), bias=mg.npy(dw.dwconv.bias), dout=mg.npy(go),
+            out=mg.npy(y), dx=mg.npy(x.grad), dweight=mg.npy(dw.dwconv.weight.grad), dbias=mg.npy(dw.dwconv.bias.grad),
+            geom=np.array([nf, H, W]))
+
 
 if __name__ == "__main__":
     main()

@@ -45,6 +45,21 @@ def test_dwconv3d_matches_conv3d(cuda_device, shape, dtype):
         assert e < tol, f"{name}: {e:.2e}"
 
 
+def test_dwconv3d_matches_reference_module_golden(cuda_device):
+    """fixture produced by the reference's own DWConv module (tests/golden/make_golden_vivim.py)."""
+    from conftest import golden
+    from vivim_b200.dwconv3d import dwconv3d_tokens
+    g = golden("vivim_dwconv")
+    nf, h, w = (int(v) for v in g["geom"])
+    x = torch.from_numpy(g["x"]).cuda().requires_grad_()
+    wt = torch.from_numpy(g["weight"]).cuda().requires_grad_()
+    b = torch.from_numpy(g["bias"]).cuda().requires_grad_()
+    y = dwconv3d_tokens(x, wt, b, nf, h, w)
+    y.backward(torch.from_numpy(g["dout"]).cuda())
+    for name, got in (("out", y), ("dx", x.grad), ("dweight", wt.grad), ("dbias", b.grad)):
+        assert rel_err(got.detach().cpu().numpy(), g[name]) < 1e-5, name
+
+
 def test_dwconv3d_without_bias_and_partial_grads(cuda_device):
     from vivim_b200.dwconv3d import dwconv3d_tokens
     torch.manual_seed(0)
