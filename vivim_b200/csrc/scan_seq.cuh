@@ -253,8 +253,9 @@ __global__ void __launch_bounds__(kSegThreads, 9) seg_agg_kernel(const vv_scan_a
 }
 
 // ================================================================ pass 2: fold segment aggregates
-// One CTA of 512 threads per row.  Thread (k, n): chunk k of the row's segments (in scan order),
-// state n.  Each thread folds its few segments, the chunk aggregates are combined through shared
+// A CTA of 512 threads serves `rows_per_cta` rows with `chunks` chunks each (chunks * N * rows_per_cta <= 512:
+// one row with 32 chunks for the long stage-1 sequences, many rows per CTA for the short late-stage ones).
+// Thread (row, k, n): chunk k of the row's segments (in scan order), state n.  Each thread folds its few segments, the chunk aggregates are combined through shared
 // memory, and a second sweep writes the state entering every segment.  Forward: carry[s] = state
 // entering segment s (chk), last_state = state after the last one; reverse: carry[s] = adjoint
 // entering segment s from the right (radj).  All loads of a thread are independent of its FMA chain.
@@ -263,18 +264,19 @@ constexpr int kCarryMaxPer = 16;   // segments a thread keeps in registers betwe
 
 template <bool kRev>
 __global__ void __launch_bounds__(kCarryThreads) seg_carry_kernel(const float2* __restrict__ agg, float* __restrict__ carry,
-                                                                  float* __restrict__ last_state, const int S, const int N) {
+                                                                  float* __restrict__ last_state, const int S, const int N,
+                                                                  const int chunks, const int rows_per_cta, const int64_t rows) {
     __shared__ float2 s_chunk[kCarryThreads];
     pdl_trigger();
     pdl_wait();   // segment aggregates of the preceding kernel
-    const int64_t row = blockIdx.x;
-    const int chunks = kCarryThreads / N;
-    const int k = threadIdx.x / N, n = threadIdx.x - k * N;
+    const int rloc = threadIdx.x / (chunks * N);
+    const int64_t row = (int64_t)blockIdx.x * rows_per_cta + rloc;
+    const int k = (threadIdx.x - rloc * chunks * N) / N, n = threadIdx.x % N;
     const int per = (S + chunks - 1) / chunks;
     const int lo = min(k * per, S), hi = min(lo + per, S);   // this thread's segments, in scan order
     const float2* __restrict__ ag = agg + row * S * N + n;
     float* __restrict__ cr = carry + row * S * N + n;
-    const bool active = k < chunks;
+    const bool active = rloc < rows_per_cta && row < rows;
     const bool cached = per <= kCarryMaxPer;
     float2 v[kCarryMaxPer];
     float P = 1.f, X = 0.f;
@@ -304,7 +306,7 @@ __global__ void __launch_bounds__(kCarryThreads) seg_carry_kernel(const float2* 
     if (!active) return;
     float E = 0.f;
     for (int kk = 0; kk < k; ++kk) {
-        const float2 w = s_chunk[kk * N + n];
+        const float2 w = s_chunk[(rloc * chunks + kk) * N + n];
         E = fmaf(w.x, E, w.y);
     }
     if (cached) {

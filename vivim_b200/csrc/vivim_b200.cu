@@ -275,9 +275,12 @@ int launch_seg_fwd(const vv_scan_args& a, const SegPlan& p, cudaStream_t st) {
 template <bool kRev>
 int launch_seg_carry(const vv_scan_args& a, const SegPlan& p, cudaStream_t st) {
     const int64_t rows = (int64_t)a.batch * a.dim;
-    launch_kernel(vv::seg_carry_kernel<kRev>, dim3((unsigned)rows), dim3(vv::kCarryThreads), 0, st,
-                  use_pdl() && (g_pass_mask & 1), reinterpret_cast<const float2*>(a.agg), kRev ? a.radj : a.chk,
-                  kRev ? (float*)nullptr : a.last_state, p.segs, a.dstate);
+    // >= 4 segments per thread when the sequence is short, at most 512 / N chunks per row
+    const int chunks = std::max(1, std::min(vv::kCarryThreads / a.dstate, (p.segs + 3) / 4));
+    const int rows_per_cta = std::max(1, vv::kCarryThreads / (chunks * a.dstate));
+    launch_kernel(vv::seg_carry_kernel<kRev>, dim3((unsigned)((rows + rows_per_cta - 1) / rows_per_cta)),
+                  dim3(vv::kCarryThreads), 0, st, use_pdl() && (g_pass_mask & 1), reinterpret_cast<const float2*>(a.agg),
+                  kRev ? a.radj : a.chk, kRev ? (float*)nullptr : a.last_state, p.segs, a.dstate, chunks, rows_per_cta, rows);
     return check_launch(kRev ? "seg_carry_kernel<rev>" : "seg_carry_kernel<fwd>");
 }
 
