@@ -365,6 +365,17 @@ def run_ours(args, rank, world, local_rank):
         if world > 1:
             dist.destroy_process_group()
         return
+    # Second roofline, the one that actually binds these kernels: MUFU.EX2 lane-operations per pass (one per state-step
+    # for the decay, plus softplus / sigmoid in the per-position pre-pass) against the measured MUFU rate
+    # (scripts/microbench/mufu_rate.cu: 15.57 lanes/clk/SM on B200) at the SM clock sampled during the run.
+    ss = clips * D_INNER * SEQLEN * D_STATE            # state-steps
+    pos = clips * D_INNER * SEQLEN                     # (channel, position) pairs
+    mufu_ops = {"fwd_agg": ss + 2 * pos, "fwd_main": ss + 2 * pos + 2 * pos, "bwd_agg": ss + 4 * pos,
+                "bwd_main": ss * 9 // 8 + 5 * pos}
+    sm_mhz = (clk.summary().get("sm_mhz") or 1965.0)
+    mufu_peak = 15.57 * 148 * sm_mhz * 1e6
+    mufu = {k: {"mufu_lane_ops": v, "floor_us": v / mufu_peak * 1e6, "frac_of_mufu_peak": v / mufu_peak / passes[k]}
+            for k, v in mufu_ops.items()}
     line = {"metric": METRIC, "value": value, "unit": "GB/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": elapsed / args.steps * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
@@ -372,6 +383,8 @@ def run_ours(args, rank, world, local_rank):
             "hbm_frac_of_measured_peak": value / world / peak,
             "roofline": roofline, "e2e": e2e, "gpu_launches": launches, "clocks": clk.summary(),
             "kernel_us": {k: v * 1e6 for k, v in passes.items()},
+            "mufu_roofline": {"peak_lane_ops_per_s": mufu_peak, "source": "scripts/microbench/mufu_rate.cu (15.57 lanes/clk/SM)",
+                              "kernels": mufu},
             "fwd_GBps_kernels_only": fwd_b / (passes["fwd_agg"] + passes["fwd_carry"] + passes["fwd_main"]) / 1e9,
             "bwd_GBps_kernels_only": bwd_b / (passes["bwd_agg"] + passes["bwd_carry"] + passes["bwd_main"]) / 1e9,
             "conv1d": conv}
