@@ -156,3 +156,27 @@ def test_scan_is_run_to_run_stable(cuda_device, shape):
             assert np.array_equal(first[k], again[k]), k
         for k in ("dA", "dB", "dC", "dD", "ddelta_bias"):
             assert np.allclose(first[k], again[k], rtol=1e-2, atol=1e-2 * np.abs(first[k]).max()), k
+
+
+def _random_configs(count, seed=2026):
+    rng = np.random.default_rng(seed)
+    out = []
+    for _ in range(count):
+        groups = int(rng.choice([1, 1, 2, 3]))
+        dim = groups * int(rng.integers(1, 25))
+        out.append((int(rng.integers(1, 4)), dim, int(rng.choice([1, 3, 63, 64, 65, 127, 200, 513, 1000])),
+                    int(rng.choice([1, 2, 4, 5, 8, 16, 17, 32])), groups,
+                    bool(rng.integers(2)), bool(rng.integers(2)), bool(rng.integers(2)), bool(rng.integers(2)),
+                    [torch.float32, torch.bfloat16, torch.float16][int(rng.integers(3))]))
+    return out
+
+
+@pytest.mark.parametrize("cfg", _random_configs(24), ids=lambda c: "-".join(str(v).replace("torch.", "") for v in c))
+def test_scan_random_configs(cuda_device, cfg):
+    """Seeded random sweep over (batch, dim, L, N, groups, D / z / bias / softplus on-off, dtype): segment
+    boundaries +-1, single-position sequences, channel counts that leave warps / channel groups partly empty,
+    state counts that pad the compile-time state block."""
+    batch, dim, seqlen, dstate, groups, has_D, has_z, has_bias, softplus, dtype = cfg
+    d = make_scan_inputs(batch, dim, seqlen, dstate, groups, dtype, seed=seqlen * 131 + dim, has_D=has_D, has_z=has_z,
+                         has_bias=has_bias)
+    compare(run_scan_cuda(d, dtype, softplus), run_scan_oracle(d, softplus), TOL[dtype], TOL_W[dtype], label=str(cfg))
