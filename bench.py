@@ -240,7 +240,7 @@ class ScanSet:
         a.B_bs = a.C_bs = N_ * L_
         a.B_gs = a.C_gs = N_ * L_
         a.B_ns = a.C_ns = L_
-        a.io_dtype, a.delta_softplus = _lib.VV_BF16, 1
+        a.io_dtype, a.delta_softplus, a.zero_accumulators = _lib.VV_BF16, 1, 1
         self.args = a
         self.n_bc = n_bc
 
@@ -249,9 +249,8 @@ class ScanSet:
 
 
 def launch_step(s, lib, stream):
-    """zero accumulators -> scan fwd (3 kernels) -> scan bwd (3 kernels) -> dB/dC cast to bf16."""
+    """scan fwd (3 kernels) -> scan bwd (3 kernels, the first one zero-fills the fp32 accumulators) -> dB/dC cast to bf16."""
     from vivim_b200 import _lib
-    s.acc.zero_()
     _lib.check(lib.vv_scan_fwd(ctypes.byref(s.args), ctypes.c_void_p(stream)), "vv_scan_fwd")
     _lib.check(lib.vv_scan_bwd(ctypes.byref(s.args), ctypes.c_void_p(stream)), "vv_scan_bwd")
     s.dBC16.view(-1).copy_(s.acc[:2 * s.n_bc])

@@ -116,6 +116,9 @@ typedef struct {
     int64_t dout_bs, dout_ds, du_bs, du_ds, ddelta_bs, ddelta_ds, dz_bs, dz_ds;
     int32_t io_dtype;       /* VV_F32 / VV_F16 / VV_BF16 */
     int32_t delta_softplus; /* 0 / 1 */
+    int32_t zero_accumulators; /* bwd: 1 = vv_scan_bwd zero-fills dA, dB, dC, dD, ddelta_bias itself (in its first kernel,
+                                  no separate memset launch); 0 = the caller has zeroed them (reference convention,
+                                  selective_scan.cpp:460-466) */
 } vv_scan_args;
 
 int vv_scan_fwd(const vv_scan_args *a, void *stream);

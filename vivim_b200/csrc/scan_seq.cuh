@@ -245,6 +245,31 @@ __global__ void __launch_bounds__(kSegThreads, 9) seg_agg_kernel(const vv_scan_a
     // tail of the preceding kernel; `agg` may still be read by it (a carry pass of an earlier call), so the
     // stores wait for its completion.
     pdl_wait();
+    if (kRev && a.zero_accumulators) {
+        // The backward's fp32 accumulators are zero-filled here, by the first kernel of vv_scan_bwd and after the
+        // dependency wait (whatever used the buffers before is complete), instead of by a memset launch of the caller:
+        // the live threads of the first channel block of a group clear the segment's dB / dC (N rows x 64 positions),
+        // lane (r, q) of the first segment of the first batch entry its channel's parameter gradients.
+        if (c.d0 == c.g * (a.dim / a.ngroups)) {
+            const int64_t base = ((int64_t)c.b * a.ngroups + c.g) * N;
+            for (int idx = threadIdx.x; idx < N * kSeg; idx += 4 * c.nrows) {
+                const int n = idx / kSeg, t = c.t0 + (idx - n * kSeg);
+                if (t < L) {
+                    a.dB[(base + n) * L + t] = 0.f;
+                    a.dC[(base + n) * L + t] = 0.f;
+                }
+            }
+        }
+        if (c.seg == 0 && c.b == 0) {
+#pragma unroll
+            for (int k = 0; k < NQ; ++k)
+                if (q * NQ + k < N) a.dA[(int64_t)d * N + q * NQ + k] = 0.f;
+            if (q == 0) {
+                if (a.dD) a.dD[d] = 0.f;
+                if (a.ddelta_bias) a.ddelta_bias[d] = 0.f;
+            }
+        }
+    }
 #pragma unroll
     for (int k = 0; k < NQ; ++k) {
         const int n = q * NQ + k;

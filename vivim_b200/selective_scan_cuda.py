@@ -132,10 +132,11 @@ def bwd(u, delta, A, B, C, D, z, delta_bias, dout, chk, dz, delta_softplus):
            "selective_scan bwd: bad checkpoint tensor")
     du = torch.empty_like(u, memory_format=torch.contiguous_format)
     ddelta = torch.empty_like(delta, memory_format=torch.contiguous_format)
-    # all fp32 accumulators live in one zero-filled buffer (one fill kernel instead of five):
-    # [dB | dC | dA | dD | ddelta_bias]
+    # all fp32 accumulators live in one buffer [dB | dC | dA | dD | ddelta_bias]; vv_scan_bwd zero-fills it in its
+    # first kernel (zero_accumulators = 1), so there is no fill launch (the reference's shim calls torch::zeros five
+    # times: selective_scan.cpp:460-466)
     n_bc = B.numel()
-    acc = torch.zeros(2 * n_bc + dim * dstate + 2 * dim, dtype=torch.float32, device=dev)
+    acc = (torch.empty if u.numel() > 0 else torch.zeros)(2 * n_bc + dim * dstate + 2 * dim, dtype=torch.float32, device=dev)
     dBC = acc[:2 * n_bc].view(2, *B.shape)
     dB, dC = dBC[0], dBC[1]
     dA = acc[2 * n_bc:2 * n_bc + dim * dstate].view(dim, dstate)
@@ -161,6 +162,7 @@ def bwd(u, delta, A, B, C, D, z, delta_bias, dout, chk, dz, delta_softplus):
         a.dA, a.dB, a.dC = dA.data_ptr(), dB.data_ptr(), dC.data_ptr()
         a.dD = dD.data_ptr() if dD is not None else None
         a.ddelta_bias = ddelta_bias.data_ptr() if ddelta_bias is not None else None
+        a.zero_accumulators = 1
         with torch.cuda.device(dev):
             stream = torch.cuda.current_stream().cuda_stream
             _lib.check(_lib.lib().vv_scan_bwd(ctypes.byref(a), ctypes.c_void_p(stream)), "vv_scan_bwd")
