@@ -20,8 +20,9 @@
 //      no decay from the neighbouring segment and shares the lane's decay product with h),
 //   2. combines the 8 lane aggregates of its channel by two interleaved 3-step shuffle scans,
 //   3. sweeps its 8 positions once more producing states, adjoints and every gradient term.
-// B and C of the segment are staged once per CTA as fp32; the four channel groups of a warp read the
-// same 128 bytes (broadcast, one wavefront per access).  dB/dC are reduced over the 4 channels of a
+// B and C of the segment are staged once per CTA as fp32 (a 128-bit shared load costs 4 wavefronts per warp
+// whether or not its four quarter-warps read the same bytes, so the four channel groups gain nothing from
+// reading the same row -- measured).  dB/dC are reduced over the 4 channels of a
 // warp by a transposing shuffle reduce-scatter (12 shuffles for 16 values), parked with ONE 128-bit
 // store per state in a warp-private tile -- no atomics, no block barrier inside the state loop --
 // and leave the CTA summed over its 16 channels as 128-bit red.global.add: D/16-way contention in

@@ -3,7 +3,7 @@
 // Used for everything that only needs the recurrence in ONE direction: the segment aggregates
 // (forward and reverse) and the whole forward pass.  Layout:
 //
-//   * the sequence is cut into SEGMENTS of 64 positions; a CTA (2 warps) owns 16 channels x one
+//   * the sequence is cut into SEGMENTS of 64 positions; a CTA (4 warps) owns 32 channels x one
 //     segment.  Four adjacent lanes share a channel and split its N states (N/4 each, in registers);
 //     every lane walks the 64 positions in order, so a state recurrence is one FMA chain and there
 //     is no cross-lane scan and no block barrier on the data path:
@@ -24,8 +24,12 @@
 //     is paid once per CTA instead of once per channel.
 //   * the forward kernel writes its outputs into a shared tile in the I/O dtype and flushes it with
 //     128-bit stores (a row segment of 128 bytes per 8 lanes).
-//   * shared memory is kept at <= 25 KB per CTA so that >= 9 CTAs (18 warps) are resident per SM and
-//     the 2560-CTA grid of the B=1 stage-1 shape runs in ~2 full waves.
+//   * the aggregate kernels need 20 KB and 56 registers, so 9 CTAs (36 warps) are resident per SM and the 1280-CTA
+//     grid of the B=1 stage-1 shape is a single wave; measured against the MUFU.EX2 rate they run at 77-89 % of
+//     peak (bench.py "mufu_roofline").  The forward kernel (35 KB: B and C tiles plus the output staging) is bound
+//     by shared-memory wavefronts instead, 11.75 per warp and position against 6 in the aggregate kernels.
+//   * launched as programmatic dependents: a kernel's loads, pre-pass and tile fills overlap the tail of its
+//     predecessor; its first access to what the predecessor wrote (or may still read) comes after the wait.
 //
 //   pass 1  seg_agg_kernel    (P, X) of every (row, segment, state), forward or reverse
 //   pass 2  seg_carry_kernel  per row: fold the segment aggregates -> state entering each segment

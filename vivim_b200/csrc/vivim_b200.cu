@@ -237,7 +237,7 @@ int set_smem(K kernel, size_t bytes) {
     return VV_OK;
 }
 
-// geometry of the segment kernels (scan_seq.cuh): 16 channels x one 64-position segment per CTA
+// geometry of the segment kernels (scan_seq.cuh): 32 channels x one 64-position segment per CTA
 struct SegPlan {
     int NB;        // compile-time state block: 8, 16 or 32
     int segs;
