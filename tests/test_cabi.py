@@ -36,13 +36,15 @@ def test_exports_every_declared_symbol(L):
 def test_struct_layout_matches_c(tmp_path):
     src = tmp_path / "sz.c"
     src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "vivim_b200.h"\n'
-                   'int main(){printf("%zu %zu %zu %zu\\n", sizeof(vv_scan_args), sizeof(vv_conv1d_args),'
-                   ' offsetof(vv_scan_args, io_dtype), offsetof(vv_conv1d_args, silu));return 0;}\n')
+                   'int main(){printf("%zu %zu %zu %zu %zu %zu %zu\\n", sizeof(vv_scan_args), sizeof(vv_conv1d_args),'
+                   ' offsetof(vv_scan_args, io_dtype), offsetof(vv_conv1d_args, silu), sizeof(vv_dwconv3d_args),'
+                   ' offsetof(vv_scan_args, zero_accumulators), offsetof(vv_dwconv3d_args, io_dtype));return 0;}\n')
     exe = tmp_path / "sz"
     subprocess.run(["/usr/bin/gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
     got = [int(v) for v in subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split()]
     assert got == [ctypes.sizeof(_lib.ScanArgs), ctypes.sizeof(_lib.ConvArgs),
-                   _lib.ScanArgs.io_dtype.offset, _lib.ConvArgs.silu.offset]
+                   _lib.ScanArgs.io_dtype.offset, _lib.ConvArgs.silu.offset, ctypes.sizeof(_lib.DwConv3dArgs),
+                   _lib.ScanArgs.zero_accumulators.offset, _lib.DwConv3dArgs.io_dtype.offset]
 
 
 def test_version_and_units(L):
@@ -74,6 +76,10 @@ def test_bad_arguments_are_reported_not_launched(L):
     s.dstate = 64
     assert L.vv_scan_fwd(ctypes.byref(s), None) == -2  # valid for the reference, not served here
     assert L.vv_last_launch_count() == 0
+    w = _lib.DwConv3dArgs()
+    assert L.vv_dwconv3d_fwd(ctypes.byref(w), None) == -1 and b"weight is required" in L.vv_last_error()
+    w.weight = w.x = w.out = p
+    assert L.vv_dwconv3d_fwd(ctypes.byref(w), None) == -1 and b"sizes must be positive" in L.vv_last_error()
 
 
 def test_missing_library_fails_loudly(monkeypatch):
