@@ -3,12 +3,13 @@
 // Replaces the channel-first kernels of the reference (causal-conv1d/csrc/causal_conv1d_fwd.cu:39-130,
 // causal_conv1d_bwd.cu:46-240).  Design (B200-first, not a port):
 //   * pure streaming op, HBM-bound: 2T bytes fwd, 3T bytes bwd (T = B*D*L*sizeof(io)).
-//   * one thread owns 8 consecutive positions = one 128-bit access per tensor; a warp therefore
-//     touches 512 contiguous bytes per request.  No shared-memory staging on the data path:
+//   * one thread owns 2 chunks of 8 consecutive positions (1024 positions apart) = two 128-bit accesses per
+//     tensor, all issued before the first use (memory-level parallelism is what bounds a streaming kernel
+//     this short); a warp touches 512 contiguous bytes per request.  No shared-memory staging on the data path:
 //     the (K-1)-element halo travels lane-to-lane by warp shuffle, only lane 0 / lane 31 of a
 //     warp fetch their halo from global memory (L1/L2 hits: the neighbouring warp streams it).
-//   * the grid is (rows = B*D, tiles of 1024 positions): every CTA is independent, there is no
-//     serial chunk loop, so even the B=1 stage-1 shape (128 rows x 20480) gives 2560 CTAs.
+//   * the grid is (rows = B*D, tiles of 2048 positions): every CTA is independent, there is no
+//     serial chunk loop, so even the B=1 stage-1 shape (128 rows x 20480) gives 1280 CTAs.
 //   * K in {2,3,4} is served by one 4-tap code path (leading taps zero-padded).
 //   * dweight/dbias: per-thread partial sums -> warp shuffle reduce -> 4-warp shared-memory
 //     reduce -> one fp32 atomicAdd per (CTA, tap); accumulators are zeroed by the caller exactly
@@ -21,7 +22,9 @@
 namespace vv {
 
 constexpr int kConvThreads = 128;
-constexpr int kConvTile = kConvThreads * kVecElems;  // 1024 positions per CTA
+constexpr int kConvChunks = 2;                        // 8-position chunks per thread: 2 x 16 B of every tensor in flight
+constexpr int kConvSpan = kConvThreads * kVecElems;   // 1024 positions: one chunk of every thread of the CTA
+constexpr int kConvTile = kConvSpan * kConvChunks;    // positions per CTA
 constexpr int kTaps = 4;
 
 __device__ __forceinline__ float load_weight(const void* p, int dtype, int idx) {
@@ -63,32 +66,39 @@ __global__ void __launch_bounds__(kConvThreads) conv1d_fwd_kernel(const vv_conv1
     const int row = blockIdx.x;
     const int b = row / a.dim, d = row - b * a.dim;
     const int L = a.seqlen;
-    const int t0 = blockIdx.y * kConvTile + threadIdx.x * kVecElems;
+    const int tb = blockIdx.y * kConvTile + threadIdx.x * kVecElems;
     const T* __restrict__ x = reinterpret_cast<const T*>(a.x) + b * a.x_bs + d * a.x_ds;
     T* __restrict__ out = reinterpret_cast<T*>(a.out) + b * a.out_bs + d * a.out_ds;
 
+    // all loads of the thread first (kConvChunks x 16 B in flight), then the arithmetic
+    Raw8<T, kVec> rx[kConvChunks];
+#pragma unroll
+    for (int c = 0; c < kConvChunks; ++c) rx[c].load(x, tb + c * kConvSpan, L);
     float taps[kTaps], bias;
     load_taps(a, d, taps, bias);
-
-    float xx[kTaps - 1 + 8];
-    {
-        float v[8], h[kTaps - 1];
-        load8<T, kVec>(x, t0, L, v);
-        halo_before<T>(x, t0, L, v, h);
 #pragma unroll
-        for (int j = 0; j < kTaps - 1; ++j) xx[j] = h[j];
+    for (int c = 0; c < kConvChunks; ++c) {
+        const int t0 = tb + c * kConvSpan;
+        float xx[kTaps - 1 + 8];
+        {
+            float v[8], h[kTaps - 1];
+            rx[c].unpack(v);
+            halo_before<T>(x, t0, L, v, h);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) xx[kTaps - 1 + i] = v[i];
+            for (int j = 0; j < kTaps - 1; ++j) xx[j] = h[j];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) xx[kTaps - 1 + i] = v[i];
+        }
+        float o[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            float acc = bias;
+#pragma unroll
+            for (int j = 0; j < kTaps; ++j) acc = fmaf(taps[j], xx[i + j], acc);
+            o[i] = kSilu ? acc * sigmoid_f(acc) : acc;
+        }
+        store8<T, kVec>(out, t0, L, o);
     }
-    float o[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        float acc = bias;
-#pragma unroll
-        for (int j = 0; j < kTaps; ++j) acc = fmaf(taps[j], xx[i + j], acc);
-        o[i] = kSilu ? acc * sigmoid_f(acc) : acc;
-    }
-    store8<T, kVec>(out, t0, L, o);
 }
 
 // d(pre-activation) at position t, recomputed from global memory (used for the 3-position halo to
@@ -118,68 +128,78 @@ __global__ void __launch_bounds__(kConvThreads) conv1d_bwd_kernel(const vv_conv1
     const int b = row / a.dim, d = row - b * a.dim;
     const int L = a.seqlen;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int t0 = blockIdx.y * kConvTile + threadIdx.x * kVecElems;
+    const int tb = blockIdx.y * kConvTile + threadIdx.x * kVecElems;
     const T* __restrict__ x = reinterpret_cast<const T*>(a.x) + b * a.x_bs + d * a.x_ds;
     const T* __restrict__ dout = reinterpret_cast<const T*>(a.dout) + b * a.dout_bs + d * a.dout_ds;
     T* __restrict__ dx = reinterpret_cast<T*>(a.dx) + b * a.dx_bs + d * a.dx_ds;
 
+    // all loads of the thread first (2 tensors x kConvChunks x 16 B in flight), then the arithmetic
+    Raw8<T, kVec> rx[kConvChunks], rg[kConvChunks];
+#pragma unroll
+    for (int c = 0; c < kConvChunks; ++c) {
+        rx[c].load(x, tb + c * kConvSpan, L);
+        rg[c].load(dout, tb + c * kConvSpan, L);
+    }
     float taps[kTaps], bias;
     load_taps(a, d, taps, bias);
-
-    float xx[kTaps - 1 + 8];
-    {
-        float v[8], h[kTaps - 1];
-        load8<T, kVec>(x, t0, L, v);
-        halo_before<T>(x, t0, L, v, h);
-#pragma unroll
-        for (int j = 0; j < kTaps - 1; ++j) xx[j] = h[j];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) xx[kTaps - 1 + i] = v[i];
-    }
-    // dd[0..7] = dpre of own positions, dd[8..10] = dpre of the 3 positions to the right
-    float dd[8 + kTaps - 1];
-    {
-        float g[8];
-        load8<T, kVec>(dout, t0, L, g);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            if (kSilu) {
-                float pre = bias;
-#pragma unroll
-                for (int j = 0; j < kTaps; ++j) pre = fmaf(taps[j], xx[i + j], pre);
-                const float sg = sigmoid_f(pre);
-                dd[i] = g[i] * sg * (1.f + pre * (1.f - sg));
-            } else {
-                dd[i] = g[i];
-            }
-        }
-    }
-#pragma unroll
-    for (int j = 0; j < kTaps - 1; ++j) dd[8 + j] = __shfl_down_sync(0xffffffffu, dd[j], 1);
-    if (lane == 31) {
-#pragma unroll
-        for (int j = 0; j < kTaps - 1; ++j) dd[8 + j] = dpre_at<T, kSilu>(x, dout, t0 + 8 + j, L, taps, bias);
-    }
-    // dx[s] = sum_j taps[j] * dpre[s + 3 - j]
-    float o[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        float acc = 0.f;
-#pragma unroll
-        for (int j = 0; j < kTaps; ++j) acc = fmaf(taps[j], dd[i + (kTaps - 1) - j], acc);
-        o[i] = acc;
-    }
-    store8<T, kVec>(dx, t0, L, o);
-
     // dtaps[j] = sum_t x[t - 3 + j] * dpre[t];  dbias = sum_t dpre[t]
     float part[kTaps + 1];
 #pragma unroll
     for (int j = 0; j <= kTaps; ++j) part[j] = 0.f;
+
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
+    for (int c = 0; c < kConvChunks; ++c) {
+        const int t0 = tb + c * kConvSpan;
+        float xx[kTaps - 1 + 8];
+        {
+            float v[8], h[kTaps - 1];
+            rx[c].unpack(v);
+            halo_before<T>(x, t0, L, v, h);
 #pragma unroll
-        for (int j = 0; j < kTaps; ++j) part[j] = fmaf(xx[i + j], dd[i], part[j]);
-        part[kTaps] += dd[i];
+            for (int j = 0; j < kTaps - 1; ++j) xx[j] = h[j];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) xx[kTaps - 1 + i] = v[i];
+        }
+        // dd[0..7] = dpre of own positions, dd[8..10] = dpre of the 3 positions to the right
+        float dd[8 + kTaps - 1];
+        {
+            float g[8];
+            rg[c].unpack(g);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                if (kSilu) {
+                    float pre = bias;
+#pragma unroll
+                    for (int j = 0; j < kTaps; ++j) pre = fmaf(taps[j], xx[i + j], pre);
+                    const float sg = sigmoid_f(pre);
+                    dd[i] = g[i] * sg * (1.f + pre * (1.f - sg));
+                } else {
+                    dd[i] = g[i];
+                }
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < kTaps - 1; ++j) dd[8 + j] = __shfl_down_sync(0xffffffffu, dd[j], 1);
+        if (lane == 31) {
+#pragma unroll
+            for (int j = 0; j < kTaps - 1; ++j) dd[8 + j] = dpre_at<T, kSilu>(x, dout, t0 + 8 + j, L, taps, bias);
+        }
+        // dx[s] = sum_j taps[j] * dpre[s + 3 - j]
+        float o[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            float acc = 0.f;
+#pragma unroll
+            for (int j = 0; j < kTaps; ++j) acc = fmaf(taps[j], dd[i + (kTaps - 1) - j], acc);
+            o[i] = acc;
+        }
+        store8<T, kVec>(dx, t0, L, o);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+#pragma unroll
+            for (int j = 0; j < kTaps; ++j) part[j] = fmaf(xx[i + j], dd[i], part[j]);
+            part[kTaps] += dd[i];
+        }
     }
 #pragma unroll
     for (int j = 0; j <= kTaps; ++j) part[j] = warp_sum(part[j]);
