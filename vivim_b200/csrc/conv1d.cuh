@@ -124,6 +124,7 @@ __device__ __forceinline__ float dpre_at(const T* __restrict__ x, const T* __res
 template <typename T, bool kSilu, bool kVec>
 __global__ void __launch_bounds__(kConvThreads) conv1d_bwd_kernel(const vv_conv1d_args a) {
     __shared__ float s_red[kConvThreads / 32][kTaps + 1];
+    __shared__ float s_halo[kConvChunks][kConvThreads / 32][kTaps - 1];
     const int row = blockIdx.x;
     const int b = row / a.dim, d = row - b * a.dim;
     const int L = a.seqlen;
@@ -142,47 +143,63 @@ __global__ void __launch_bounds__(kConvThreads) conv1d_bwd_kernel(const vv_conv1
     }
     float taps[kTaps], bias;
     load_taps(a, d, taps, bias);
-    // dtaps[j] = sum_t x[t - 3 + j] * dpre[t];  dbias = sum_t dpre[t]
-    float part[kTaps + 1];
-#pragma unroll
-    for (int j = 0; j <= kTaps; ++j) part[j] = 0.f;
 
+    // pass 1: own positions -- x window and d(pre-activation) of every chunk
+    float xx[kConvChunks][kTaps - 1 + 8], dd[kConvChunks][8 + kTaps - 1];
 #pragma unroll
     for (int c = 0; c < kConvChunks; ++c) {
         const int t0 = tb + c * kConvSpan;
-        float xx[kTaps - 1 + 8];
         {
             float v[8], h[kTaps - 1];
             rx[c].unpack(v);
             halo_before<T>(x, t0, L, v, h);
 #pragma unroll
-            for (int j = 0; j < kTaps - 1; ++j) xx[j] = h[j];
+            for (int j = 0; j < kTaps - 1; ++j) xx[c][j] = h[j];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) xx[kTaps - 1 + i] = v[i];
+            for (int i = 0; i < 8; ++i) xx[c][kTaps - 1 + i] = v[i];
         }
-        // dd[0..7] = dpre of own positions, dd[8..10] = dpre of the 3 positions to the right
-        float dd[8 + kTaps - 1];
-        {
-            float g[8];
-            rg[c].unpack(g);
+        float g[8];
+        rg[c].unpack(g);
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                if (kSilu) {
-                    float pre = bias;
+        for (int i = 0; i < 8; ++i) {
+            if (kSilu) {
+                float pre = bias;
 #pragma unroll
-                    for (int j = 0; j < kTaps; ++j) pre = fmaf(taps[j], xx[i + j], pre);
-                    const float sg = sigmoid_f(pre);
-                    dd[i] = g[i] * sg * (1.f + pre * (1.f - sg));
-                } else {
-                    dd[i] = g[i];
-                }
+                for (int j = 0; j < kTaps; ++j) pre = fmaf(taps[j], xx[c][i + j], pre);
+                const float sg = sigmoid_f(pre);
+                dd[c][i] = g[i] * sg * (1.f + pre * (1.f - sg));
+            } else {
+                dd[c][i] = g[i];
             }
         }
+        // the first 3 values of every warp are the right halo of the warp before it: through shared memory
+        if (lane == 0) {
 #pragma unroll
-        for (int j = 0; j < kTaps - 1; ++j) dd[8 + j] = __shfl_down_sync(0xffffffffu, dd[j], 1);
+            for (int j = 0; j < kTaps - 1; ++j) s_halo[c][warp][j] = dd[c][j];
+        }
+    }
+    __syncthreads();
+    // pass 2: dd[8..10] = d(pre-activation) of the 3 positions to the right (next lane / next warp / next chunk;
+    // only the last warp of the last chunk recomputes them from global memory), dx, parameter-gradient partials
+    // dtaps[j] = sum_t x[t - 3 + j] * dpre[t];  dbias = sum_t dpre[t]
+    float part[kTaps + 1];
+#pragma unroll
+    for (int j = 0; j <= kTaps; ++j) part[j] = 0.f;
+#pragma unroll
+    for (int c = 0; c < kConvChunks; ++c) {
+        const int t0 = tb + c * kConvSpan;
+#pragma unroll
+        for (int j = 0; j < kTaps - 1; ++j) dd[c][8 + j] = __shfl_down_sync(0xffffffffu, dd[c][j], 1);
         if (lane == 31) {
+            constexpr int kWarps = kConvThreads / 32;
+            if (warp + 1 < kWarps || c + 1 < kConvChunks) {
+                const int cn = warp + 1 < kWarps ? c : c + 1, wn = warp + 1 < kWarps ? warp + 1 : 0;
 #pragma unroll
-            for (int j = 0; j < kTaps - 1; ++j) dd[8 + j] = dpre_at<T, kSilu>(x, dout, t0 + 8 + j, L, taps, bias);
+                for (int j = 0; j < kTaps - 1; ++j) dd[c][8 + j] = s_halo[cn < kConvChunks ? cn : 0][wn][j];
+            } else {
+#pragma unroll
+                for (int j = 0; j < kTaps - 1; ++j) dd[c][8 + j] = dpre_at<T, kSilu>(x, dout, t0 + 8 + j, L, taps, bias);
+            }
         }
         // dx[s] = sum_j taps[j] * dpre[s + 3 - j]
         float o[8];
@@ -190,15 +207,15 @@ __global__ void __launch_bounds__(kConvThreads) conv1d_bwd_kernel(const vv_conv1
         for (int i = 0; i < 8; ++i) {
             float acc = 0.f;
 #pragma unroll
-            for (int j = 0; j < kTaps; ++j) acc = fmaf(taps[j], dd[i + (kTaps - 1) - j], acc);
+            for (int j = 0; j < kTaps; ++j) acc = fmaf(taps[j], dd[c][i + (kTaps - 1) - j], acc);
             o[i] = acc;
         }
         store8<T, kVec>(dx, t0, L, o);
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
 #pragma unroll
-            for (int j = 0; j < kTaps; ++j) part[j] = fmaf(xx[i + j], dd[i], part[j]);
-            part[kTaps] += dd[i];
+            for (int j = 0; j < kTaps; ++j) part[j] = fmaf(xx[c][i + j], dd[c][i], part[j]);
+            part[kTaps] += dd[c][i];
         }
     }
 #pragma unroll
