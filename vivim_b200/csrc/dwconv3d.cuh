@@ -112,27 +112,56 @@ template <> struct DwRaw<__half, true> {
     __device__ __forceinline__ float2 get() const { return unpack_pair<__half>(r); }
 };
 
-// the 3 rows (y-1, y, y+1) of frame fs of the column's window: positions x0-1 .. x0+kDwX, zeros outside the volume
+// Addressing of a thread's column, hoisted out of the frame walk (the first version recomputed a 64-bit address and
+// the bounds of every read: 4600 instructions per warp, 42 % of them on the ALU pipe): the element offset of
+// (b, frame 0, y, x = 0, c), the frame stride, and the frame-independent offsets / validity of the 3 rows and
+// kDwX + 2 positions of the window.  A read is then one 32-bit add, one widening multiply-add and the load.
 template <typename T, bool kPair>
-__device__ __forceinline__ void dw_frame(const T* __restrict__ in, const DwGeom& g, const DwCoord& k, int fs,
-                                         DwRaw<T, kPair> (&win)[3][kDwX + 2]) {
+struct DwWindow {
+    int64_t col, fstride;
+    int yoff[3], xoff[kDwX + 2];
+    bool yok[3], xok[kDwX + 2];
+    int c, C;
+    __device__ __forceinline__ DwWindow(const DwGeom& g, const DwCoord& k) : c(k.c), C(g.C) {
+        col = (((int64_t)k.b * g.T * g.H + k.y) * g.W) * g.C + k.c;
+        fstride = (int64_t)g.H * g.W * g.C;
 #pragma unroll
-    for (int dy = 0; dy < 3; ++dy) {
-        const int ys = k.y + dy - 1;
-        const bool ok = (unsigned)ys < (unsigned)g.H;
-        const T* row = in + ((((int64_t)k.b * g.T + fs) * g.H + (ok ? ys : 0)) * g.W) * g.C + k.c;
+        for (int dy = 0; dy < 3; ++dy) {
+            yoff[dy] = (dy - 1) * g.W * g.C;
+            yok[dy] = (unsigned)(k.y + dy - 1) < (unsigned)g.H;
+        }
 #pragma unroll
         for (int j = 0; j < kDwX + 2; ++j) {
-            const int xs = k.x0 + j - 1;
-            win[dy][j].load(row + (int64_t)xs * g.C, k.c, g.C, ok && (unsigned)xs < (unsigned)g.W);
+            xoff[j] = (k.x0 + j - 1) * g.C;
+            xok[j] = (unsigned)(k.x0 + j - 1) < (unsigned)g.W;
         }
     }
-}
+    // the 3 rows (y-1, y, y+1) of frame f: positions x0-1 .. x0+kDwX, zeros outside the volume
+    __device__ __forceinline__ void load(const T* __restrict__ in, int f, DwRaw<T, kPair> (&win)[3][kDwX + 2]) const {
+        const T* fb = in + col + f * fstride;
+#pragma unroll
+        for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+            for (int j = 0; j < kDwX + 2; ++j) win[dy][j].load(fb + (yoff[dy] + xoff[j]), c, C, yok[dy] && xok[j]);
+    }
+    // positions x0 .. x0+kDwX-1 of row y of frame f
+    __device__ __forceinline__ void store(T* __restrict__ out, int f, const float2 (&v)[kDwX]) const {
+        T* fb = out + col + f * fstride;
+#pragma unroll
+        for (int j = 0; j < kDwX; ++j)
+            if (xok[j + 1]) dw_st<T, kPair>(fb + xoff[j + 1], c, C, v[j]);
+    }
+    __device__ __forceinline__ void load_row(const T* __restrict__ in, int f, bool fok, float2 (&v)[kDwX]) const {
+        const T* fb = in + col + (fok ? f : 0) * fstride;
+#pragma unroll
+        for (int j = 0; j < kDwX; ++j) v[j] = (fok && xok[j + 1]) ? dw_ld<T, kPair>(fb + xoff[j + 1], c, C) : make_float2(0.f, 0.f);
+    }
+};
 
 // kMirror = false: forward (+ bias).  kMirror = true: input gradient (weights mirrored, no bias).
 // weight: fp32 (27, C), tap-major; tap = (dt * 3 + dy) * 3 + dx.
 template <typename T, bool kPair, bool kMirror>
-__global__ void __launch_bounds__(kDwThreads) dwconv3d_kernel(const T* __restrict__ in, const float* __restrict__ weight,
+__global__ void __launch_bounds__(kDwThreads, 2) dwconv3d_kernel(const T* __restrict__ in, const float* __restrict__ weight,
                                                               const float* __restrict__ bias, T* __restrict__ out,
                                                               const DwGeom g) {
     const DwCoord k = dw_coord(g, (int64_t)blockIdx.x * kDwThreads + threadIdx.x);
@@ -143,6 +172,7 @@ __global__ void __launch_bounds__(kDwThreads) dwconv3d_kernel(const T* __restric
     for (int t = 0; t < 27; ++t) w[t] = dw_ldw(weight + (int64_t)(kMirror ? 26 - t : t) * g.C + k.c, k.c, g.C, wpair);
     const float2 b2 = (!kMirror && bias) ? dw_ldw(bias + k.c, k.c, g.C, wpair) : make_float2(0.f, 0.f);
 
+    const DwWindow<T, kPair> win_at(g, k);
     // a0: output frame f-1, a1: frame f, a2: frame f+1 while input frame f is being scattered
     float2 a0[kDwX], a1[kDwX], a2[kDwX];
 #pragma unroll
@@ -151,7 +181,7 @@ __global__ void __launch_bounds__(kDwThreads) dwconv3d_kernel(const T* __restric
 #pragma unroll 1
     for (int f = 0; f < g.T; ++f) {
         DwRaw<T, kPair> raw[3][kDwX + 2];
-        dw_frame<T, kPair>(in, g, k, f, raw);
+        win_at.load(in, f, raw);
 #pragma unroll
         for (int dy = 0; dy < 3; ++dy) {
             float2 win[kDwX + 2];
@@ -168,12 +198,7 @@ __global__ void __launch_bounds__(kDwThreads) dwconv3d_kernel(const T* __restric
                 }
             }
         }
-        if (f > 0) {
-            T* row = out + ((((int64_t)k.b * g.T + f - 1) * g.H + k.y) * g.W) * g.C + k.c;
-#pragma unroll
-            for (int j = 0; j < kDwX; ++j)
-                if (k.x0 + j < g.W) dw_st<T, kPair>(row + (int64_t)(k.x0 + j) * g.C, k.c, g.C, a0[j]);
-        }
+        if (f > 0) win_at.store(out, f - 1, a0);
 #pragma unroll
         for (int j = 0; j < kDwX; ++j) {
             a0[j] = a1[j];
@@ -181,10 +206,7 @@ __global__ void __launch_bounds__(kDwThreads) dwconv3d_kernel(const T* __restric
             a2[j] = b2;
         }
     }
-    T* row = out + ((((int64_t)k.b * g.T + g.T - 1) * g.H + k.y) * g.W) * g.C + k.c;
-#pragma unroll
-    for (int j = 0; j < kDwX; ++j)
-        if (k.x0 + j < g.W) dw_st<T, kPair>(row + (int64_t)(k.x0 + j) * g.C, k.c, g.C, a0[j]);
+    win_at.store(out, g.T - 1, a0);
 }
 
 // weight / bias gradient: block (32 lanes = 64 channels, kDwCols columns), grid (ceil(C / 64), column blocks)
@@ -209,21 +231,16 @@ __global__ void __launch_bounds__(32 * kDwCols) dwconv3d_wgrad_kernel(const T* _
             k.y = (int)(r % g.H);
             k.b = (int)(r / g.H);
             // dout of the column for frames f-1, f, f+1 (zeros outside the clip)
+            const DwWindow<T, kPair> win_at(g, k);
             float2 g0[kDwX], g1[kDwX], g2[kDwX];
-            auto load_g = [&](int f, float2 (&dst)[kDwX]) {
-                const T* row = dout + ((((int64_t)k.b * g.T + (f < g.T ? f : 0)) * g.H + k.y) * g.W) * g.C + k.c;
-#pragma unroll
-                for (int j = 0; j < kDwX; ++j)
-                    dst[j] = (f < g.T && k.x0 + j < g.W) ? dw_ld<T, kPair>(row + (int64_t)(k.x0 + j) * g.C, k.c, g.C)
-                                                         : make_float2(0.f, 0.f);
-            };
+            auto load_g = [&](int f, float2 (&dst)[kDwX]) { win_at.load_row(dout, f, f < g.T, dst); };
 #pragma unroll
             for (int j = 0; j < kDwX; ++j) g0[j] = make_float2(0.f, 0.f);
             load_g(0, g1);
 #pragma unroll 1
             for (int f = 0; f < g.T; ++f) {
                 DwRaw<T, kPair> raw[3][kDwX + 2];
-                dw_frame<T, kPair>(x, g, k, f, raw);
+                win_at.load(x, f, raw);
                 load_g(f + 1, g2);
 #pragma unroll
                 for (int j = 0; j < kDwX; ++j) accb = add2(accb, g1[j]);
