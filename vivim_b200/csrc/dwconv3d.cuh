@@ -217,7 +217,7 @@ __global__ void __launch_bounds__(32 * kDwCols) dwconv3d_wgrad_kernel(const T* _
     __shared__ float2 red[kDwCols][32];
     const int lane = threadIdx.x, col = threadIdx.y;
     const int xt = (g.W + kDwX - 1) / kDwX;
-    const int64_t ncols = (int64_t)g.B * g.H * xt;
+    const int ncols = g.B * g.H * xt;
     DwCoord k;
     k.c = (blockIdx.x * 32 + lane) * 2;
     k.live = k.c < g.C;
@@ -225,11 +225,11 @@ __global__ void __launch_bounds__(32 * kDwCols) dwconv3d_wgrad_kernel(const T* _
 #pragma unroll
     for (int t = 0; t < 27; ++t) acc[t] = make_float2(0.f, 0.f);
     if (k.live) {
-        for (int64_t ci = (int64_t)blockIdx.y * kDwCols + col; ci < ncols; ci += (int64_t)gridDim.y * kDwCols) {
-            int64_t r = ci;
-            k.x0 = (int)(r % xt) * kDwX; r /= xt;
-            k.y = (int)(r % g.H);
-            k.b = (int)(r / g.H);
+        for (int ci = blockIdx.y * kDwCols + col; ci < ncols; ci += gridDim.y * kDwCols) {   // 32-bit: no division routines
+            const int r1 = ci / xt, r2 = r1 / g.H;
+            k.x0 = (ci - r1 * xt) * kDwX;
+            k.y = r1 - r2 * g.H;
+            k.b = r2;
             // dout of the column for frames f-1, f, f+1 (zeros outside the clip)
             const DwWindow<T, kPair> win_at(g, k);
             float2 g0[kDwX], g1[kDwX], g2[kDwX];

@@ -147,6 +147,8 @@ int launch_dw(const vv_dwconv3d_args* a, void* stream) {
     if (kBwd && a->dbias && !a->dweight) return fail(VV_ERR_BAD_ARG, "dwconv3d_bwd: dbias needs dweight");
     if (a->batch <= 0 || a->frames <= 0 || a->height <= 0 || a->width <= 0 || a->channels <= 0)
         return fail(VV_ERR_BAD_ARG, "dwconv3d: sizes must be positive");
+    if ((int64_t)a->batch * a->height * a->width > (1ll << 30))
+        return fail(VV_ERR_UNSUPPORTED, "dwconv3d: more than 2^30 (batch, y, x) columns");
     if (!valid_dtype(a->io_dtype)) return fail(VV_ERR_BAD_ARG, "dwconv3d: dtype must be fp32, fp16 or bf16");
     const int es = elem_size(a->io_dtype);
     if (!elem_aligned(a->x, es) || !elem_aligned(a->out, es) || !elem_aligned(a->dout, es) || !elem_aligned(a->dx, es))
