@@ -180,3 +180,31 @@ def test_scan_random_configs(cuda_device, cfg):
     d = make_scan_inputs(batch, dim, seqlen, dstate, groups, dtype, seed=seqlen * 131 + dim, has_D=has_D, has_z=has_z,
                          has_bias=has_bias)
     compare(run_scan_cuda(d, dtype, softplus), run_scan_oracle(d, softplus), TOL[dtype], TOL_W[dtype], label=str(cfg))
+
+
+def test_scan_back_to_back_calls_do_not_interfere(cuda_device):
+    """The kernels are chained with programmatic dependent launch (a kernel's prologue overlaps the tail of its
+    predecessor) and the caching allocator hands consecutive calls the same workspaces: results of calls issued
+    back to back on alternating inputs must equal the results of the same calls issued one at a time."""
+    sets = [make_scan_inputs(2, 48, 1536, 16, 1, torch.bfloat16, seed=s) for s in (3, 4)]
+    isolated = []
+    for d in sets:
+        torch.cuda.synchronize()
+        isolated.append(run_scan_cuda(d, torch.bfloat16))
+        torch.cuda.synchronize()
+    from mamba_ssm.ops.selective_scan_interface import selective_scan_fn
+    from gpu_util import dev
+    pending = []
+    for it in range(12):                       # no synchronisation inside this loop
+        d = sets[it % 2]
+        t = {k: dev(d[k], torch.bfloat16 if k in ("u", "delta", "B", "C", "z") else torch.float32, grad=True)
+             for k in ("u", "delta", "A", "B", "C", "D", "z", "delta_bias")}
+        out = selective_scan_fn(t["u"], t["delta"], t["A"], t["B"], t["C"], t["D"], z=t["z"],
+                                delta_bias=t["delta_bias"], delta_softplus=True)
+        out.backward(dev(d["dout"], torch.bfloat16))
+        pending.append((it % 2, out.detach(), t["u"].grad, t["delta"].grad, t["z"].grad))
+    torch.cuda.synchronize()
+    for which, out, du, ddelta, dz in pending:
+        ref = isolated[which]
+        for name, got in (("out", out), ("du", du), ("ddelta", ddelta), ("dz", dz)):
+            assert np.array_equal(got.float().cpu().numpy(), ref[name]), name
