@@ -79,6 +79,18 @@ def main():
             depths=np.array(DEPTHS), seed=np.array(SEED))
     print("logits", tuple(logits.shape), "params", sum(v.numel() for v in sd.values()))
 
+    # the reference Mamba(v3) at the REAL stage-1 size (d_model 64, L = 5*64*64 tokens): the fixture keeps the seeds and
+    # every 61st output token (parameters are reproduced from the seed: the constructors draw identically)
+    torch.manual_seed(SEED + 5)
+    m = ms.Mamba(d_model=64, d_state=16, d_conv=4, expand=2, bimamba_type="v3", nframes=5).eval()
+    gx = torch.Generator().manual_seed(SEED + 6)
+    xs = torch.randn(1, 5 * 64 * 64, 64, generator=gx)
+    with torch.no_grad():
+        ys = m(xs)
+    mg.save("mamba_stage1_full", y_sub=mg.npy(ys[:, ::61]), stride=np.array(61), seed_model=np.array(SEED + 5),
+            seed_input=np.array(SEED + 6), y_absmax=np.array(float(ys.abs().max())))
+    print("stage-1 Mamba forward", tuple(ys.shape), "absmax", float(ys.abs().max()))
+
     # the reference's own DWConv module (modeling/vivim.py:57-68), forward + autograd gradients, on a tiny token tensor
     torch.manual_seed(SEED + 2)
     dw = ref_vivim.DWConv(dim=12)
