@@ -116,6 +116,10 @@ typedef struct {
     int64_t dout_bs, dout_ds, du_bs, du_ds, ddelta_bs, ddelta_ds, dz_bs, dz_ds;
     int32_t io_dtype;       /* VV_F32 / VV_F16 / VV_BF16 */
     int32_t delta_softplus; /* 0 / 1 */
+    /* bwd, optional: dB / dC additionally in the I/O dtype (B,G,N,L contiguous) -- the cast the reference's shim performs
+     * with `.to(B.dtype)` (selective_scan.cpp:488), as a fourth kernel chained to the backward with programmatic
+     * dependent launch instead of a separate framework op.  NULL = fp32 dB / dC only. */
+    void *dB_io, *dC_io;
     int32_t zero_accumulators; /* bwd: 1 = vv_scan_bwd zero-fills dA, dB, dC, dD, ddelta_bias itself (in its first kernel,
                                   no separate memset launch); 0 = the caller has zeroed them (reference convention,
                                   selective_scan.cpp:460-466) */
@@ -152,7 +156,7 @@ int vv_last_launch_count(void);
 
 /* Measurement aid (bench.py, ncu): restrict which of the three scan passes subsequent vv_scan_fwd /
  * vv_scan_bwd calls on this thread launch.  bit0: segment aggregates, bit1: carry fold, bit2: main
- * kernel.  Default 7 (all).  Returns the previous mask.  Workspaces must hold valid data from an
+ * kernel, bit3: the dB/dC cast of vv_scan_bwd.  Default 15 (all).  Returns the previous mask.  Workspaces must hold valid data from an
  * earlier full call when a pass is skipped. */
 int vv_scan_set_pass_mask(int mask);
 

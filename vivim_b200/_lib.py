@@ -45,7 +45,8 @@ class ScanArgs(Structure):
         ("C_bs", c_int64), ("C_gs", c_int64), ("C_ns", c_int64),
         ("dout_bs", c_int64), ("dout_ds", c_int64), ("du_bs", c_int64), ("du_ds", c_int64),
         ("ddelta_bs", c_int64), ("ddelta_ds", c_int64), ("dz_bs", c_int64), ("dz_ds", c_int64),
-        ("io_dtype", c_int32), ("delta_softplus", c_int32), ("zero_accumulators", c_int32),
+        ("io_dtype", c_int32), ("delta_softplus", c_int32),
+        ("dB_io", c_void_p), ("dC_io", c_void_p), ("zero_accumulators", c_int32),
     ]
 
 

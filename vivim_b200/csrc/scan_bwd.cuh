@@ -429,4 +429,21 @@ __global__ void __launch_bounds__(kBwdThreads, 4) seg_bwd_kernel(const vv_scan_a
     }
 }
 
+// fp32 dB / dC -> I/O dtype, 8 elements per thread; chained to seg_bwd_kernel as a programmatic dependent
+template <typename T>
+__global__ void __launch_bounds__(256) cast_bc_kernel(const float* __restrict__ dB, const float* __restrict__ dC,
+                                                      T* __restrict__ oB, T* __restrict__ oC, const int64_t n) {
+    pdl_wait();
+    const int64_t i = ((int64_t)blockIdx.x * 256 + threadIdx.x) * 8;
+    const float* src = blockIdx.y ? dC : dB;
+    T* dst = blockIdx.y ? oC : oB;
+    if (i + 8 <= n && (reinterpret_cast<uintptr_t>(src + i) % 16 == 0) && (reinterpret_cast<uintptr_t>(dst + i) % 16 == 0)) {
+        float v[8];
+        load8_vec<float>(src + i, v);
+        store8_vec<T>(dst + i, v);
+    } else {
+        for (int64_t k = i; k < n && k < i + 8; ++k) dst[k] = from_f32<T>(src[k]);
+    }
+}
+
 }  // namespace vv

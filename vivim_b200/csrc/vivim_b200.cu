@@ -17,7 +17,7 @@ namespace {
 
 thread_local char g_err[512] = "";
 thread_local int g_launches = 0;
-thread_local int g_pass_mask = 7;
+thread_local int g_pass_mask = 15;
 
 int fail(int code, const char* fmt, ...) {
     va_list ap;
@@ -204,6 +204,7 @@ int check_scan_common(const vv_scan_args* a, bool bwd) {
         if (!a->dout || !a->du || !a->ddelta || !a->dA || !a->dB || !a->dC || !a->radj)
             return fail(VV_ERR_BAD_ARG, "scan_bwd: dout, du, ddelta, dA, dB, dC, radj are required");
         if (a->z && !a->dz) return fail(VV_ERR_BAD_ARG, "scan_bwd: dz is required when z is given");
+        if ((a->dB_io != nullptr) != (a->dC_io != nullptr)) return fail(VV_ERR_BAD_ARG, "scan_bwd: dB_io and dC_io need each other");
         if (a->D && !a->dD) return fail(VV_ERR_BAD_ARG, "scan_bwd: dD is required when D is given");
         if (a->delta_bias && !a->ddelta_bias) return fail(VV_ERR_BAD_ARG, "scan_bwd: ddelta_bias is required when delta_bias is given");
     }
@@ -333,6 +334,15 @@ int scan_bwd_t(const vv_scan_args& a, cudaStream_t st) {
         });
         if ((rc = check_launch("seg_bwd_kernel")) != VV_OK) return rc;
     }
+    if ((g_pass_mask & 8) && a.dB_io != nullptr) {
+        {
+            const int64_t n = (int64_t)a.batch * a.ngroups * a.dstate * a.seqlen;
+            const dim3 cgrid((unsigned)((n + 2047) / 2048), 2);
+            launch_kernel(vv::cast_bc_kernel<T>, cgrid, dim3(256), 0, st, use_pdl() && (g_pass_mask & 4), (const float*)a.dB, (const float*)a.dC,
+                          reinterpret_cast<T*>(a.dB_io), reinterpret_cast<T*>(a.dC_io), n);
+            if ((rc = check_launch("cast_bc_kernel")) != VV_OK) return rc;
+        }
+    }
     return VV_OK;
 }
 
@@ -365,7 +375,7 @@ const char* vv_last_error(void) { return g_err; }
 int vv_last_launch_count(void) { return g_launches; }
 int vv_scan_set_pass_mask(int mask) {
     const int prev = g_pass_mask;
-    g_pass_mask = mask & 7;
+    g_pass_mask = mask & 15;
     return prev;
 }
 int vv_scan_num_segments(int seqlen) { return seqlen <= 0 ? 0 : (seqlen + VV_SCAN_SEGMENT - 1) / VV_SCAN_SEGMENT; }

@@ -163,11 +163,15 @@ def bwd(u, delta, A, B, C, D, z, delta_bias, dout, chk, dz, delta_softplus):
         a.dD = dD.data_ptr() if dD is not None else None
         a.ddelta_bias = ddelta_bias.data_ptr() if ddelta_bias is not None else None
         a.zero_accumulators = 1
+        if B.dtype != torch.float32:   # dB / dC in the dtype of B / C: converted by a kernel chained to the backward
+            dBC_io = torch.empty((2, *B.shape), dtype=B.dtype, device=dev)
+            a.dB_io, a.dC_io = dBC_io[0].data_ptr(), dBC_io[1].data_ptr()
         with torch.cuda.device(dev):
             stream = torch.cuda.current_stream().cuda_stream
             _lib.check(_lib.lib().vv_scan_bwd(ctypes.byref(a), ctypes.c_void_p(stream)), "vv_scan_bwd")
         LAUNCHES += 3
-    dBC = dBC.to(B.dtype)   # fp32 accumulation, then one cast (selective_scan.cpp:461-462, 488)
+    # fp32 accumulation, then one cast (selective_scan.cpp:461-462, 488)
+    dBC = dBC_io if (u.numel() > 0 and B.dtype != torch.float32) else dBC.to(B.dtype)
     res = [du, ddelta, dA, dBC[0], dBC[1], dD, ddelta_bias]
     if z is not None:
         res.append(dz)
