@@ -100,23 +100,11 @@ elif args.mode == "train":
         return loss
 elif args.full_graph:
     # inference: the whole forward as one CUDA graph (static input / output buffers)
-    model.eval()
-    static_out = None
-    side = torch.cuda.Stream(dev)
-    side.wait_stream(torch.cuda.current_stream())
-    with torch.cuda.stream(side), torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16, cache_enabled=False):
-        for _ in range(3):
-            model(clip)
-    torch.cuda.current_stream().wait_stream(side)
-    torch.cuda.synchronize()
-    fgraph = torch.cuda.CUDAGraph()
-    with torch.cuda.graph(fgraph), torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16, cache_enabled=False):
-        static_out = model(clip)
-    mean_buf = torch.zeros((), device=dev)
+    from vivim_b200.graphed import InferenceGraph
+    infer = InferenceGraph(model.eval(), (clip,), autocast_dtype=torch.bfloat16)
 
     def step():
-        fgraph.replay()
-        return static_out.float().mean()
+        return infer().float().mean()
 else:
     model.eval()
 

@@ -83,3 +83,18 @@ def test_whole_step_graph_matches_eager_gradients(cuda_device):
         loss = float(step(x, t))
         assert abs(loss - loss_ref) <= 1e-3 * abs(loss_ref)
         assert rel_err(step.flat_grad.cpu().numpy(), grad_ref.cpu().numpy()) < 1e-2
+
+
+@pytest.mark.gpu
+def test_inference_graph_matches_eager(cuda_device):
+    """vivim_b200.graphed.InferenceGraph: the whole-network forward replayed as one CUDA graph equals the eager
+    forward bit for bit, also after the static input has been replaced."""
+    from vivim_b200.graphed import InferenceGraph
+    g = golden("vivim_model")
+    model = _build(g).cuda().eval()
+    clips = [torch.from_numpy(g["clip"]).cuda(), torch.randn(*g["clip"].shape, device="cuda")]
+    with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
+        want = [model(c).float().cpu().numpy() for c in clips]
+    infer = InferenceGraph(model, (clips[0],), autocast_dtype=torch.bfloat16)
+    for c, w in zip(clips, want):
+        assert np.array_equal(infer(c).float().cpu().numpy(), w)
