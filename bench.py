@@ -329,13 +329,15 @@ def run_ours(args, rank, world, local_rank):
     for bwd in (0, 1):
         fn = lib.vv_scan_bwd if bwd else lib.vv_scan_fwd
         for bit, name in ((1, "agg"), (2, "carry"), (4, "main")):
-            lib.vv_scan_set_pass_mask(bit)
+            for s in sets:
+                s.args.pass_mask = bit
             run = lambda i: _lib.check(fn(ctypes.byref(sets[i % n_sets].args), ctypes.c_void_p(stream)), "scan pass")  # noqa: E731
             for i in range(3):
                 run(i)
             torch.cuda.synchronize()
             passes[("bwd_" if bwd else "fwd_") + name] = time_events(run, reps, torch) / reps
-    lib.vv_scan_set_pass_mask(15)
+    for s in sets:
+        s.args.pass_mask = 0
     launches += 6 * (reps + 3)
     t_main = passes["bwd_main"]
     peak, peak_src = measured_peak()

@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define VV_VERSION 100 /* 0.1.0 */
+#define VV_VERSION 200 /* 0.2.0 */
 
 /* element type of the streamed (B,D,L)/(B,G,N,L) tensors */
 enum { VV_F32 = 0, VV_F16 = 1, VV_BF16 = 2 };
@@ -40,6 +40,16 @@ enum {
     VV_ERR_UNSUPPORTED = -2,  /* valid for the reference, not served by these kernels */
     VV_ERR_ALIGN = -3         /* pointer not aligned to its element size */
 };
+
+/* Traversal order of a direction (Mamba.forward v3, mamba/mamba_ssm/modules/mamba_simple.py:217-264).  Tensors always
+ * stay in MEMORY order; a direction only changes the order in which the recurrence / the causal taps visit the tokens:
+ *   VV_DIR_FWD     j -> j                                   (mamba_simple.py:217-229)
+ *   VV_DIR_REV     j -> L-1-j                               (xz.flip([-1]), :230-242)
+ *   VV_DIR_FRAMES  j -> (j % nframes) * (L/nframes) + j / nframes
+ *                  tokens are (frame, pixel) in memory and are visited pixel-major: the
+ *                  chunk(nframes) / stack(-1) / flatten(-2) copy of :243-247 */
+enum { VV_DIR_FWD = 0, VV_DIR_REV = 1, VV_DIR_FRAMES = 2 };
+#define VV_MAX_DIRS 4
 
 /* Sequence positions per checkpoint segment: scan states are checkpointed / carried every 64
  * positions; one segment x 16 channels is the work unit of a CTA in every scan kernel. */
@@ -73,6 +83,34 @@ typedef struct {
 
 int vv_conv1d_fwd(const vv_conv1d_args *a, void *stream);
 int vv_conv1d_bwd(const vv_conv1d_args *a, void *stream);
+
+/* ------------------------------------------------------------------ causal conv1d of several directions, one launch
+ * Replaces the per-direction causal_conv1d_fwd / _bwd calls of Mamba.forward v3 (mamba_simple.py:217-260 ->
+ * selective_scan_interface.py:177, 239, 281-283) together with the xz.flip / frame-interleave copies that feed them:
+ * ONE read of x produces the conv output of every direction, in memory order;
+ *   out[b, k*D + d, m(j)] = act(bias[k,d] + sum_i w[k,d,i] * x[b, d, m_k(j - (K-1) + i)])      m_k: traversal of direction k
+ * and the backward sums the input gradient of all directions into one dx.
+ */
+typedef struct {
+    const void *x;       /* (B,D,L) io_dtype, strides (x_bs, x_ds, 1) */
+    const float *weight; /* (ndirs,D,K) float32 contiguous */
+    const float *bias;   /* (ndirs,D) float32 contiguous, or NULL */
+    void *out;           /* fwd: (B,ndirs*D,L) io_dtype, strides (out_bs, out_ds, 1) */
+    const void *dout;    /* bwd: (B,ndirs*D,L) io_dtype, strides (dout_bs, dout_ds, 1) */
+    void *dx;            /* bwd: (B,D,L) io_dtype, strides (dx_bs, dx_ds, 1): sum over the directions; may be a view */
+    float *dweight;      /* bwd: (ndirs,D,K) float32 += */
+    float *dbias;        /* bwd: (ndirs,D) float32 +=, or NULL */
+    int32_t batch, dim, seqlen, width; /* dim = D (channels of x); width K in {2,3,4} */
+    int32_t ndirs;                     /* 1..VV_MAX_DIRS */
+    int32_t dir_mode[VV_MAX_DIRS];     /* VV_DIR_* per direction */
+    int32_t nframes;                   /* VV_DIR_FRAMES: frames per clip (divides seqlen); else ignored */
+    int64_t x_bs, x_ds, out_bs, out_ds, dout_bs, dout_ds, dx_bs, dx_ds;
+    int32_t io_dtype;                  /* VV_F32 / VV_F16 / VV_BF16 */
+    int32_t silu;                      /* 0: identity, 1: SiLU */
+} vv_conv1d_dirs_args;
+
+int vv_conv1d_dirs_fwd(const vv_conv1d_dirs_args *a, void *stream);
+int vv_conv1d_dirs_bwd(const vv_conv1d_dirs_args *a, void *stream);
 
 /* ------------------------------------------------------------------ selective scan
  * Replaces selective_scan_cuda.fwd / .bwd for real A and input-dependent B and C
@@ -123,6 +161,29 @@ typedef struct {
     int32_t zero_accumulators; /* bwd: 1 = vv_scan_bwd zero-fills dA, dB, dC, dD, ddelta_bias itself (in its first kernel,
                                   no separate memset launch); 0 = the caller has zeroed them (reference convention,
                                   selective_scan.cpp:460-466) */
+    /* ---- directions (all zero = one left-to-right scan, the reference op) --------------------------------------
+     * ndirs > 1: the `dim` channels are ndirs direction blocks of dim/ndirs channels (ngroups % ndirs == 0, the groups
+     * are split evenly over the blocks); block k visits the tokens in order dir_mode[k].  This is Mamba.forward v3's
+     * three mamba_inner_fn_no_out_proj calls (mamba_simple.py:217-260) as ONE launch over channel-concatenated
+     * parameters, without the flip / interleave copies.  agg / chk / radj and the fp32 dB / dC accumulators are indexed
+     * by TRAVERSAL position; every I/O tensor (u, delta, z, B, C, out*, dout, du, ddelta, dz, dB_io, dC_io) by MEMORY
+     * position. */
+    int32_t ndirs;                  /* 0 or 1: single direction dir_mode[0] */
+    int32_t dir_mode[VV_MAX_DIRS];  /* VV_DIR_* */
+    int32_t nframes;                /* VV_DIR_FRAMES: frames per clip (divides seqlen) */
+    /* B / C sequence stride.  0 or 1: (B,G,N,L) layout, unit sequence stride (B_ns = state stride).  > 1: position-major,
+     * e.g. straight out of x_proj's GEMM output x_dbl (B*L, R+2N) (selective_scan_interface.py:181-207 transposes
+     * it instead): B_ns = 1, B_ls = R+2N, B_gs / B_bs accordingly. */
+    int64_t B_ls, C_ls;
+    /* dB_io / dC_io strides (elements); all zero = (B,G,N,L) contiguous.  Position-major = written straight into the
+     * dx_dbl slices that selective_scan_interface.py:255-271 fills through two transposes. */
+    int64_t dBio_bs, dBio_gs, dBio_ns, dBio_ls, dCio_bs, dCio_gs, dCio_ns, dCio_ls;
+    /* > 0: z and dout have only gate_rows channel rows, shared by the direction blocks (row = d % gate_rows): the
+     * three directions of v3 are gated by the same z and receive the same upstream gradient. */
+    int32_t gate_rows;
+    /* Measurement aid (bench.py, ncu): which passes to launch.  0 = all.  bit0: segment aggregates, bit1: carry fold,
+     * bit2: main kernel, bit3: dB/dC cast.  Skipped passes need valid workspaces from an earlier full call. */
+    int32_t pass_mask;
 } vv_scan_args;
 
 int vv_scan_fwd(const vv_scan_args *a, void *stream);
@@ -154,11 +215,10 @@ int vv_dwconv3d_bwd(const vv_dwconv3d_args *a, void *stream);
 /* number of kernel launches the last successful call on this thread enqueued (for bench.py) */
 int vv_last_launch_count(void);
 
-/* Measurement aid (bench.py, ncu): restrict which of the three scan passes subsequent vv_scan_fwd /
- * vv_scan_bwd calls on this thread launch.  bit0: segment aggregates, bit1: carry fold, bit2: main
- * kernel, bit3: the dB/dC cast of vv_scan_bwd.  Default 15 (all).  Returns the previous mask.  Workspaces must hold valid data from an
- * earlier full call when a pass is skipped. */
-int vv_scan_set_pass_mask(int mask);
+/* Test aid: 1 = every kernel takes its element-wise I/O path even where 128-bit accesses are legal (the two paths
+ * must agree bit for bit, tests/test_scan_gpu.py).  Initialised once from the environment variable
+ * VV_FORCE_SCALAR_IO; returns the previous value.  Process-wide. */
+int vv_debug_force_scalar_io(int on);
 
 #ifdef __cplusplus
 }

@@ -34,21 +34,29 @@ def test_exports_every_declared_symbol(L):
 
 
 def test_struct_layout_matches_c(tmp_path):
+    """sizeof and the offset of EVERY field of every args struct, compiled from the header with gcc."""
+    structs = {"vv_scan_args": _lib.ScanArgs, "vv_conv1d_args": _lib.ConvArgs,
+               "vv_conv1d_dirs_args": _lib.ConvDirsArgs, "vv_dwconv3d_args": _lib.DwConv3dArgs}
+    lines = []
+    for cname, cls in structs.items():
+        lines.append(f'printf("%zu\\n", sizeof({cname}));')
+        for fname, _ in cls._fields_:
+            lines.append(f'printf("%zu\\n", offsetof({cname}, {fname}));')
     src = tmp_path / "sz.c"
-    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "vivim_b200.h"\n'
-                   'int main(){printf("%zu %zu %zu %zu %zu %zu %zu\\n", sizeof(vv_scan_args), sizeof(vv_conv1d_args),'
-                   ' offsetof(vv_scan_args, io_dtype), offsetof(vv_conv1d_args, silu), sizeof(vv_dwconv3d_args),'
-                   ' offsetof(vv_scan_args, zero_accumulators), offsetof(vv_dwconv3d_args, io_dtype));return 0;}\n')
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "vivim_b200.h"\nint main(){' + "".join(lines)
+                   + "return 0;}\n")
     exe = tmp_path / "sz"
     subprocess.run(["/usr/bin/gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
     got = [int(v) for v in subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split()]
-    assert got == [ctypes.sizeof(_lib.ScanArgs), ctypes.sizeof(_lib.ConvArgs),
-                   _lib.ScanArgs.io_dtype.offset, _lib.ConvArgs.silu.offset, ctypes.sizeof(_lib.DwConv3dArgs),
-                   _lib.ScanArgs.zero_accumulators.offset, _lib.DwConv3dArgs.io_dtype.offset]
+    want = []
+    for cls in structs.values():
+        want.append(ctypes.sizeof(cls))
+        want += [getattr(cls, fname).offset for fname, _ in cls._fields_]
+    assert got == want
 
 
 def test_version_and_units(L):
-    assert L.vv_version() == 100
+    assert L.vv_version() == 200
     assert L.vv_scan_num_segments(20480) == 320
     assert L.vv_scan_num_segments(1) == 1 and L.vv_scan_num_segments(65) == 2 and L.vv_scan_num_segments(0) == 0
 
@@ -76,6 +84,20 @@ def test_bad_arguments_are_reported_not_launched(L):
     s.dstate = 64
     assert L.vv_scan_fwd(ctypes.byref(s), None) == -2  # valid for the reference, not served here
     assert L.vv_last_launch_count() == 0
+    # directions: bad mode / frames that do not divide the sequence are argument errors
+    s.dstate = 16
+    s.ndirs, s.ngroups, s.dim = 3, 3, 3
+    s.dir_mode[2] = 7
+    assert L.vv_scan_fwd(ctypes.byref(s), None) == -1 and b"dir_mode" in L.vv_last_error()
+    s.dir_mode[2] = _lib.VV_DIR_FRAMES
+    s.nframes = 5
+    assert L.vv_scan_fwd(ctypes.byref(s), None) == -1 and b"nframes" in L.vv_last_error()
+    c = _lib.ConvDirsArgs()
+    assert L.vv_conv1d_dirs_fwd(ctypes.byref(c), None) == -1
+    c.x = c.weight = c.out = p
+    c.batch = c.dim = 1
+    c.seqlen, c.width, c.ndirs = 8, 4, 5
+    assert L.vv_conv1d_dirs_fwd(ctypes.byref(c), None) == -1 and b"ndirs" in L.vv_last_error()
     w = _lib.DwConv3dArgs()
     assert L.vv_dwconv3d_fwd(ctypes.byref(w), None) == -1 and b"weight is required" in L.vv_last_error()
     w.weight = w.x = w.out = p

@@ -58,12 +58,16 @@ def test_scan_vivim_stage1_full_size_fp32(cuda_device):
     compare(run_scan_cuda(d, torch.float32), run_scan_oracle(d), TOL[torch.float32], label="stage1 fp32")
 
 
-def test_scan_scalar_io_path_equals_vector_path(cuda_device, monkeypatch):
+def test_scan_scalar_io_path_equals_vector_path(cuda_device):
     """128-bit and element-wise loaders must give bit-identical results (same arithmetic order)."""
+    from vivim_b200 import _lib
     d = make_scan_inputs(2, 8, 1024, 16, 1, torch.bfloat16, seed=3)
     a = run_scan_cuda(d, torch.bfloat16)
-    monkeypatch.setenv("VV_FORCE_SCALAR_IO", "1")
-    b = run_scan_cuda(d, torch.bfloat16)
+    prev = _lib.lib().vv_debug_force_scalar_io(1)
+    try:
+        b = run_scan_cuda(d, torch.bfloat16)
+    finally:
+        _lib.lib().vv_debug_force_scalar_io(prev)
     for k in ("out", "du", "ddelta", "dz", "last_state"):
         assert np.array_equal(a[k], b[k]), k
 

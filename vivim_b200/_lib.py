@@ -10,6 +10,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "lib", "libvivim_b200.so")
 
 VV_F32, VV_F16, VV_BF16 = 0, 1, 2
+VV_DIR_FWD, VV_DIR_REV, VV_DIR_FRAMES = 0, 1, 2
+VV_MAX_DIRS = 4
 VV_SCAN_SEGMENT = 64
 
 
@@ -22,6 +24,19 @@ class ConvArgs(Structure):
         ("x_bs", c_int64), ("x_ds", c_int64), ("out_bs", c_int64), ("out_ds", c_int64),
         ("dout_bs", c_int64), ("dout_ds", c_int64), ("dx_bs", c_int64), ("dx_ds", c_int64),
         ("io_dtype", c_int32), ("w_dtype", c_int32), ("silu", c_int32),
+    ]
+
+
+class ConvDirsArgs(Structure):
+    """vv_conv1d_dirs_args"""
+    _fields_ = [
+        ("x", c_void_p), ("weight", c_void_p), ("bias", c_void_p), ("out", c_void_p),
+        ("dout", c_void_p), ("dx", c_void_p), ("dweight", c_void_p), ("dbias", c_void_p),
+        ("batch", c_int32), ("dim", c_int32), ("seqlen", c_int32), ("width", c_int32),
+        ("ndirs", c_int32), ("dir_mode", c_int32 * VV_MAX_DIRS), ("nframes", c_int32),
+        ("x_bs", c_int64), ("x_ds", c_int64), ("out_bs", c_int64), ("out_ds", c_int64),
+        ("dout_bs", c_int64), ("dout_ds", c_int64), ("dx_bs", c_int64), ("dx_ds", c_int64),
+        ("io_dtype", c_int32), ("silu", c_int32),
     ]
 
 
@@ -47,6 +62,11 @@ class ScanArgs(Structure):
         ("ddelta_bs", c_int64), ("ddelta_ds", c_int64), ("dz_bs", c_int64), ("dz_ds", c_int64),
         ("io_dtype", c_int32), ("delta_softplus", c_int32),
         ("dB_io", c_void_p), ("dC_io", c_void_p), ("zero_accumulators", c_int32),
+        ("ndirs", c_int32), ("dir_mode", c_int32 * VV_MAX_DIRS), ("nframes", c_int32),
+        ("B_ls", c_int64), ("C_ls", c_int64),
+        ("dBio_bs", c_int64), ("dBio_gs", c_int64), ("dBio_ns", c_int64), ("dBio_ls", c_int64),
+        ("dCio_bs", c_int64), ("dCio_gs", c_int64), ("dCio_ns", c_int64), ("dCio_ls", c_int64),
+        ("gate_rows", c_int32), ("pass_mask", c_int32),
     ]
 
 
@@ -62,8 +82,8 @@ class DwConv3dArgs(Structure):
 
 # every symbol include/vivim_b200.h declares (checked by tests/test_cabi.py)
 EXPORTS = ("vv_version", "vv_last_error", "vv_scan_num_segments", "vv_conv1d_fwd", "vv_conv1d_bwd",
-           "vv_scan_fwd", "vv_scan_bwd", "vv_last_launch_count", "vv_scan_set_pass_mask",
-           "vv_dwconv3d_fwd", "vv_dwconv3d_bwd")
+           "vv_conv1d_dirs_fwd", "vv_conv1d_dirs_bwd", "vv_scan_fwd", "vv_scan_bwd", "vv_last_launch_count",
+           "vv_debug_force_scalar_io", "vv_dwconv3d_fwd", "vv_dwconv3d_bwd")
 
 _lib = None
 
@@ -79,11 +99,12 @@ def lib() -> ctypes.CDLL:
         L.vv_version.restype = c_int
         L.vv_last_error.restype = c_char_p
         L.vv_last_launch_count.restype = c_int
-        L.vv_scan_set_pass_mask.argtypes = [c_int]
-        L.vv_scan_set_pass_mask.restype = c_int
+        L.vv_debug_force_scalar_io.argtypes = [c_int]
+        L.vv_debug_force_scalar_io.restype = c_int
         L.vv_scan_num_segments.argtypes = [c_int]
         L.vv_scan_num_segments.restype = c_int
         for name, argt in (("vv_conv1d_fwd", ConvArgs), ("vv_conv1d_bwd", ConvArgs),
+                           ("vv_conv1d_dirs_fwd", ConvDirsArgs), ("vv_conv1d_dirs_bwd", ConvDirsArgs),
                            ("vv_scan_fwd", ScanArgs), ("vv_scan_bwd", ScanArgs),
                            ("vv_dwconv3d_fwd", DwConv3dArgs), ("vv_dwconv3d_bwd", DwConv3dArgs)):
             fn = getattr(L, name)

@@ -6,6 +6,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "../../include/vivim_b200.h"
+
 namespace vv {
 
 constexpr int kWarp = 32;
@@ -142,6 +144,43 @@ __device__ __forceinline__ void store8(T* __restrict__ row, int t0, int L, const
     }
 }
 
+// ---------------------------------------------------------------- traversal order
+// A scan / conv direction visits the L tokens of a row in TRAVERSAL order j = 0..L-1; every (.., L) tensor stays in
+// MEMORY order.  Trav maps j to the memory index (reference: the three directions of Mamba.forward v3,
+// mamba/mamba_ssm/modules/mamba_simple.py:217-264, which materialise xz.flip(-1) and the (t, hw) -> (hw, t) copy):
+//   VV_DIR_FWD     m = j
+//   VV_DIR_REV     m = L - 1 - j                                   (xz.flip([-1]))
+//   VV_DIR_FRAMES  m = (j % nf) * (L / nf) + j / nf                (tokens (frame, pixel) visited pixel-major)
+struct Trav {
+    int mode, L, nf, hw;
+    __device__ __forceinline__ int mem(int j) const {
+        if (mode == VV_DIR_FWD) return j;
+        if (mode == VV_DIR_REV) return L - 1 - j;
+        const int p = j / nf;
+        return (j - p * nf) * hw + p;
+    }
+};
+
+__device__ __forceinline__ uint32_t swap_halves(uint32_t w) { return __byte_perm(w, 0, 0x1032); }
+
+// positions [j0, j0+8) of traversal order -> memory (kVec: L % 8 == 0, j0 % 8 == 0, row 16-byte aligned)
+template <typename T, bool kVec>
+__device__ __forceinline__ void store8_trav(T* __restrict__ row, int j0, const Trav& tr, const float (&v)[8]) {
+    if (tr.mode == VV_DIR_FWD) { store8<T, kVec>(row, j0, tr.L, v); return; }
+    if (kVec && tr.mode == VV_DIR_REV) {
+        if (j0 < tr.L) {
+            const float r[8] = {v[7], v[6], v[5], v[4], v[3], v[2], v[1], v[0]};
+            store8_vec<T>(row + (tr.L - 8 - j0), r);
+        }
+        return;
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int j = j0 + i;
+        if (j < tr.L) row[tr.mem(j)] = from_f32<T>(v[i]);
+    }
+}
+
 // ---------------------------------------------------------------- deferred unpacking
 // Raw8 holds the 8 positions of a row segment as loaded (16 or 32 bytes of registers), so that a
 // kernel can issue ALL of its global loads first and convert later: the DRAM latency of a
@@ -154,6 +193,39 @@ template <typename T> struct Raw8<T, true> {
         if (t0 >= 0 && t0 < L) {
             lo = __ldg(reinterpret_cast<const uint4*>(row + t0));
             if (sizeof(T) == 4) hi = __ldg(reinterpret_cast<const uint4*>(row + t0) + 1);
+        }
+    }
+    // positions [j0, j0+8) in traversal order (all inside or all outside [0, L): L % 8 == 0, j0 % 8 == 0)
+    __device__ __forceinline__ void load_trav(const T* __restrict__ row, int j0, const Trav& tr) {
+        if (tr.mode == VV_DIR_FWD) { load(row, j0, tr.L); return; }
+        lo = hi = make_uint4(0, 0, 0, 0);
+        if (j0 < 0 || j0 >= tr.L) return;
+        if (tr.mode == VV_DIR_REV) {
+            const T* p = row + (tr.L - 8 - j0);          // the same 8 tokens, ascending memory order
+            const uint4 a = __ldg(reinterpret_cast<const uint4*>(p));
+            if (sizeof(T) == 4) {
+                const uint4 b = __ldg(reinterpret_cast<const uint4*>(p) + 1);
+                lo = make_uint4(b.w, b.z, b.y, b.x);
+                hi = make_uint4(a.w, a.z, a.y, a.x);
+            } else {
+                lo = make_uint4(swap_halves(a.w), swap_halves(a.z), swap_halves(a.y), swap_halves(a.x));
+            }
+            return;
+        }
+        int p = j0 / tr.nf, t = j0 - p * tr.nf;
+        uint32_t w[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const T* q = row + (int64_t)t * tr.hw + p;
+            if (sizeof(T) == 4) w[i] = __ldg(reinterpret_cast<const uint32_t*>(q));
+            else w[i] = __ldg(reinterpret_cast<const unsigned short*>(q));
+            if (++t == tr.nf) { t = 0; ++p; }
+        }
+        if (sizeof(T) == 4) {
+            lo = make_uint4(w[0], w[1], w[2], w[3]);
+            hi = make_uint4(w[4], w[5], w[6], w[7]);
+        } else {
+            lo = make_uint4(w[0] | (w[1] << 16), w[2] | (w[3] << 16), w[4] | (w[5] << 16), w[6] | (w[7] << 16));
         }
     }
     __device__ __forceinline__ void unpack(float (&v)[8]) const {
@@ -185,6 +257,13 @@ template <typename T> struct Raw8<T, false> {
             f[i] = (t >= 0 && t < L) ? to_f32<T>(row[t]) : 0.f;
         }
     }
+    __device__ __forceinline__ void load_trav(const T* __restrict__ row, int j0, const Trav& tr) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int j = j0 + i;
+            f[i] = (j >= 0 && j < tr.L) ? to_f32<T>(row[tr.mem(j)]) : 0.f;
+        }
+    }
     __device__ __forceinline__ void unpack(float (&v)[8]) const {
 #pragma unroll
         for (int i = 0; i < 8; ++i) v[i] = f[i];
@@ -208,15 +287,6 @@ __device__ __forceinline__ float softplus_f(float v) {
     const float r = e < 0.02f ? small : big;
     return v <= 20.f ? r : v;
 }
-
-// Asynchronous 16-byte global->shared copy (LDGSTS): no registers held while the data is in flight.
-// src_bytes == 0 zero-fills the destination (used for positions outside [0, L)).
-__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc, int src_bytes) {
-    const unsigned dst = (unsigned)__cvta_generic_to_shared(smem_dst);
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(dst), "l"(gsrc), "r"(src_bytes) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
 
 // Programmatic dependent launch (griddepcontrol): a kernel launched with the PDL attribute may begin
 // before its stream predecessor has finished.  pdl_trigger() lets the successor's CTAs be

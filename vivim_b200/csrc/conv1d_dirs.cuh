@@ -1,0 +1,257 @@
+// conv1d_dirs.cuh -- causal depthwise conv1d of all scan directions of a Temporal Mamba block in one launch (sm_100a).
+//
+// Reference: Mamba.forward v3 (mamba/mamba_ssm/modules/mamba_simple.py:217-260) runs causal_conv1d_fwd three times, on
+// xz, on xz.flip([-1]) and on the frame-interleaved copy of xz, each with its own weights
+// (selective_scan_interface.py:177), and the backward runs the conv forward again plus causal_conv1d_bwd three times
+// (:239, :281-283) and sums the three dx through the flip / permute backward copies.
+//
+// Here a direction is an addressing mode (Trav, common.cuh): a CTA stages ONE fp32 tile of x -- all frames x a run of
+// pixels, with a 3-position halo on both sides -- in shared memory and produces from it the conv output of every
+// direction, written in MEMORY order:
+//     forward   reads T bytes, writes ndirs * T          (the reference: ndirs * 2T plus 4T of flip / interleave copies)
+//     backward  reads (1 + ndirs) * T, writes T          (the reference: ndirs * 3T plus the copies and the dx sums)
+// Layout of the work: x is (B, D, L) with L = nf * HW tokens (frame, pixel); a CTA owns (row, pixels [p0, p0 + pt)) for
+// all nf frames; thread i of the CTA owns pixels p0 + i, p0 + i + 128, ...: consecutive threads read consecutive
+// shared-memory words (no bank conflicts) and write consecutive global elements.
+//   FWD     out[m] = bias + sum_i w[i] x[m - 3 + i]                      taps to the left in memory
+//   REV     out[m] = bias + sum_i w[i] x[m + 3 - i]                      taps to the right
+//   FRAMES  token (t, p) is position j = p nf + t of the traversal; tap j - k lives at frame t - k of the same pixel,
+//           or, wrapped, at frame t - k + s nf of pixel p - s
+// The backward stages the tile of x and one tile of d(pre-activation) per direction, then every thread gathers the input
+// gradient of its pixels from the three tiles; parameter gradients: per-thread partial sums -> warp shuffle -> shared
+// memory -> one fp32 atomicAdd per (CTA, direction, tap).
+#pragma once
+
+#include "../../include/vivim_b200.h"
+#include "common.cuh"
+
+namespace vv {
+
+constexpr int kDirsThreads = 128;
+constexpr int kDirsHalo = 4;          // 3 halo positions + 1 pad word: the tile body starts 16-byte aligned
+constexpr int kDirsMaxFrames = 16;
+
+struct DirsGeom {
+    int L, nf, hw, pt, pitch;   // pitch = pt + 2 * kDirsHalo floats per frame row of a tile
+    int p0;                     // first pixel of the CTA
+};
+
+// x (or any tile) at frame t, local pixel q in [-kDirsHalo, pt + kDirsHalo)
+__device__ __forceinline__ float tile_at(const float* __restrict__ tile, const DirsGeom& g, int t, int q) {
+    return tile[t * g.pitch + kDirsHalo + q];
+}
+
+// Stage rows [t*hw + p0 - 3, t*hw + p0 + pt + 3) of `row` (memory order, zero outside [0, L)) for every frame t.
+template <typename T, bool kVec>
+__device__ __forceinline__ void stage_tile(float* __restrict__ tile, const T* __restrict__ row, const DirsGeom& g) {
+    if (kVec) {
+        const int chunks = g.pt / 8;
+        for (int idx = threadIdx.x; idx < g.nf * chunks; idx += kDirsThreads) {
+            const int t = idx / chunks, c = idx - t * chunks;
+            const int m = t * g.hw + g.p0 + c * 8;
+            float v[8];
+            load8<T, true>(row, m, g.L, v);
+            float* dst = tile + t * g.pitch + kDirsHalo + c * 8;
+            reinterpret_cast<float4*>(dst)[0] = make_float4(v[0], v[1], v[2], v[3]);
+            reinterpret_cast<float4*>(dst)[1] = make_float4(v[4], v[5], v[6], v[7]);
+        }
+        for (int idx = threadIdx.x; idx < g.nf * 2 * (kDirsHalo - 1); idx += kDirsThreads) {
+            const int t = idx / (2 * (kDirsHalo - 1)), h = idx - t * 2 * (kDirsHalo - 1);
+            const int q = h < kDirsHalo - 1 ? h - (kDirsHalo - 1) : g.pt + h - (kDirsHalo - 1);
+            const int m = t * g.hw + g.p0 + q;
+            tile[t * g.pitch + kDirsHalo + q] = (m >= 0 && m < g.L) ? to_f32<T>(row[m]) : 0.f;
+        }
+    } else {
+        const int span = g.pt + 2 * (kDirsHalo - 1);
+        for (int idx = threadIdx.x; idx < g.nf * span; idx += kDirsThreads) {
+            const int t = idx / span, q = idx - t * span - (kDirsHalo - 1);
+            const int m = t * g.hw + g.p0 + q;
+            tile[t * g.pitch + kDirsHalo + q] = (m >= 0 && m < g.L) ? to_f32<T>(row[m]) : 0.f;
+        }
+    }
+}
+
+// Source of tap k (k positions back in traversal order) of token (t, q): frame ts, local pixel qs; false = before the
+// start of the sequence (reads as zero).  FWD / REV stay in the frame row (rows are contiguous in memory).
+__device__ __forceinline__ bool tap_source(int mode, const DirsGeom& g, int t, int q, int k, int& ts, int& qs) {
+    if (mode == VV_DIR_FWD) { ts = t; qs = q - k; return t * g.hw + g.p0 + qs >= 0; }
+    if (mode == VV_DIR_REV) { ts = t; qs = q + k; return t * g.hw + g.p0 + qs < g.L; }
+    const int s = k > t ? (k - t + g.nf - 1) / g.nf : 0;     // pixels to step back
+    ts = t - k + s * g.nf;
+    qs = q - s;
+    return g.p0 + qs >= 0;
+}
+
+// Token that reads token (t, q) through tap k (the inverse of tap_source): false = beyond the end of the sequence.
+__device__ __forceinline__ bool tap_reader(int mode, const DirsGeom& g, int t, int q, int k, int& tr, int& qr) {
+    if (mode == VV_DIR_FWD) { tr = t; qr = q + k; return t * g.hw + g.p0 + qr < g.L; }
+    if (mode == VV_DIR_REV) { tr = t; qr = q - k; return t * g.hw + g.p0 + qr >= 0; }
+    const int s = (t + k) / g.nf;
+    tr = t + k - s * g.nf;
+    qr = q + s;
+    return g.p0 + qr < g.hw;
+}
+
+// pre-activation of direction `mode` at token (t, q); taps[i] multiplies the token kTaps-1-i positions back
+__device__ __forceinline__ float pre_at(const float* __restrict__ xs, const DirsGeom& g, int mode, int t, int q,
+                                        const float (&taps)[4], float bias) {
+    float acc = bias;
+#pragma unroll
+    for (int k = 3; k >= 0; --k) {   // oldest tap first: the summation order of conv1d_fwd_kernel (bit-identical results)
+        int ts, qs;
+        if (tap_source(mode, g, t, q, k, ts, qs)) acc = fmaf(taps[3 - k], tile_at(xs, g, ts, qs), acc);
+    }
+    return acc;
+}
+
+__device__ __forceinline__ void load_dir_taps(const vv_conv1d_dirs_args& a, int k, int d, float (&taps)[4], float& bias) {
+    const int K = a.width;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int i = j - (4 - K);
+        taps[j] = i >= 0 ? a.weight[((int64_t)k * a.dim + d) * K + i] : 0.f;
+    }
+    bias = a.bias ? a.bias[(int64_t)k * a.dim + d] : 0.f;
+}
+
+__device__ __forceinline__ DirsGeom dirs_geom(const vv_conv1d_dirs_args& a, int pt) {
+    DirsGeom g;
+    g.L = a.seqlen;
+    g.nf = a.nframes > 0 ? a.nframes : 1;
+    g.hw = a.seqlen / g.nf;
+    g.pt = pt;
+    g.pitch = pt + 2 * kDirsHalo;
+    g.p0 = blockIdx.y * pt;
+    return g;
+}
+
+// smem: [x tile: nf x pitch floats]
+template <typename T, bool kSilu, bool kVec>
+__global__ void __launch_bounds__(kDirsThreads) conv1d_dirs_fwd_kernel(const vv_conv1d_dirs_args a, const int pt) {
+    extern __shared__ __align__(16) float dirs_smem[];
+    float* xs = dirs_smem;
+    const DirsGeom g = dirs_geom(a, pt);
+    const int row = blockIdx.x;
+    const int b = row / a.dim, d = row - b * a.dim;
+    stage_tile<T, kVec>(xs, reinterpret_cast<const T*>(a.x) + b * a.x_bs + d * a.x_ds, g);
+    __syncthreads();
+    for (int k = 0; k < a.ndirs; ++k) {
+        const int mode = a.dir_mode[k];
+        float taps[4], bias;
+        load_dir_taps(a, k, d, taps, bias);
+        T* __restrict__ out = reinterpret_cast<T*>(a.out) + b * a.out_bs + ((int64_t)k * a.dim + d) * a.out_ds;
+        for (int t = 0; t < g.nf; ++t) {
+            for (int q = threadIdx.x; q < g.pt; q += kDirsThreads) {
+                if (g.p0 + q >= g.hw) break;
+                float v = pre_at(xs, g, mode, t, q, taps, bias);
+                if (kSilu) v *= sigmoid_f(v);
+                out[t * g.hw + g.p0 + q] = from_f32<T>(v);
+            }
+        }
+    }
+}
+
+// smem: [x tile][d(pre) tile of direction 0][1][...]  (ndirs + 1 tiles of nf x pitch floats), [16 x 5 reduction words]
+template <typename T, bool kSilu, bool kVec>
+__global__ void __launch_bounds__(kDirsThreads) conv1d_dirs_bwd_kernel(const vv_conv1d_dirs_args a, const int pt) {
+    extern __shared__ __align__(16) float dirs_smem[];
+    const DirsGeom g = dirs_geom(a, pt);
+    const int tile_words = g.nf * g.pitch;
+    float* xs = dirs_smem;
+    float* red = dirs_smem + (a.ndirs + 1) * tile_words;       // [warp][dir][5]
+    const int row = blockIdx.x;
+    const int b = row / a.dim, d = row - b * a.dim;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    stage_tile<T, kVec>(xs, reinterpret_cast<const T*>(a.x) + b * a.x_bs + d * a.x_ds, g);
+    for (int k = 0; k < a.ndirs; ++k)
+        stage_tile<T, kVec>(xs + (k + 1) * tile_words,
+                            reinterpret_cast<const T*>(a.dout) + b * a.dout_bs + ((int64_t)k * a.dim + d) * a.dout_ds, g);
+    __syncthreads();
+    // ---- dout -> d(pre-activation), in place, body and halo; parameter-gradient partial sums over the body
+    const int span = g.pt + 2 * (kDirsHalo - 1);
+    for (int k = 0; k < a.ndirs; ++k) {
+        const int mode = a.dir_mode[k];
+        float taps[4], bias;
+        load_dir_taps(a, k, d, taps, bias);
+        float* dp = xs + (k + 1) * tile_words;
+        float part[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+        for (int t = 0; t < g.nf; ++t) {
+            for (int qq = threadIdx.x; qq < span; qq += kDirsThreads) {
+                const int q = qq - (kDirsHalo - 1);
+                const int p = g.p0 + q, m = t * g.hw + p;
+                // a token exists in this direction's sequence iff its memory index is in range (FWD / REV: rows are
+                // contiguous, a halo position may belong to the neighbouring frame) / its pixel is (FRAMES)
+                const bool exists = mode == VV_DIR_FRAMES ? (p >= 0 && p < g.hw) : (m >= 0 && m < g.L);
+                // d(pre) is only consumed towards the readers of the body: to the right for FWD / FRAMES, to the left for REV
+                const bool needed = mode == VV_DIR_REV ? q < g.pt : q >= 0;
+                float gr = 0.f;
+                if (exists && needed) {
+                    gr = dp[t * g.pitch + kDirsHalo + q];
+                    if (kSilu) {
+                        const float pre = pre_at(xs, g, mode, t, q, taps, bias);
+                        const float sg = sigmoid_f(pre);
+                        gr *= sg * (1.f + pre * (1.f - sg));
+                    }
+                }
+                dp[t * g.pitch + kDirsHalo + q] = gr;
+                if (q >= 0 && q < g.pt && p < g.hw) {       // body: this CTA owns the token
+                    part[4] += gr;
+#pragma unroll
+                    for (int kk = 0; kk < 4; ++kk) {
+                        int ts, qs;
+                        if (tap_source(mode, g, t, q, kk, ts, qs)) part[3 - kk] = fmaf(gr, tile_at(xs, g, ts, qs), part[3 - kk]);
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 5; ++j) part[j] = warp_sum(part[j]);
+        if (lane == 0) {
+#pragma unroll
+            for (int j = 0; j < 5; ++j) red[(warp * VV_MAX_DIRS + k) * 5 + j] = part[j];
+        }
+    }
+    __syncthreads();
+    // ---- dx: every direction's readers of this token
+    float wd[VV_MAX_DIRS][4];
+#pragma unroll
+    for (int k = 0; k < VV_MAX_DIRS; ++k) {
+        float bias_unused;
+        if (k < a.ndirs) load_dir_taps(a, k, d, wd[k], bias_unused);
+    }
+    T* __restrict__ dx = reinterpret_cast<T*>(a.dx) + b * a.dx_bs + d * a.dx_ds;
+    for (int t = 0; t < g.nf; ++t) {
+        for (int q = threadIdx.x; q < g.pt; q += kDirsThreads) {
+            if (g.p0 + q >= g.hw) break;
+            float acc = 0.f;
+#pragma unroll
+            for (int k = 0; k < VV_MAX_DIRS; ++k) {
+                if (k < a.ndirs) {
+                    const int mode = a.dir_mode[k];
+                    const float* dp = xs + (k + 1) * tile_words;
+#pragma unroll
+                    for (int kk = 0; kk < 4; ++kk) {
+                        int tr, qr;
+                        if (tap_reader(mode, g, t, q, kk, tr, qr)) acc = fmaf(wd[k][3 - kk], tile_at(dp, g, tr, qr), acc);
+                    }
+                }
+            }
+            dx[t * g.hw + g.p0 + q] = from_f32<T>(acc);
+        }
+    }
+    // ---- parameter gradients of the CTA
+    if (threadIdx.x < a.ndirs * 5) {
+        const int k = threadIdx.x / 5, j = threadIdx.x - k * 5;
+        float s = 0.f;
+#pragma unroll
+        for (int w = 0; w < kDirsThreads / 32; ++w) s += red[(w * VV_MAX_DIRS + k) * 5 + j];
+        if (j == 4) {
+            if (a.dbias) atomicAdd(a.dbias + (int64_t)k * a.dim + d, s);
+        } else {
+            const int i = j - (4 - a.width);
+            if (i >= 0) atomicAdd(a.dweight + ((int64_t)k * a.dim + d) * a.width + i, s);
+        }
+    }
+}
+
+}  // namespace vv

@@ -166,7 +166,7 @@ __global__ void __launch_bounds__(kDwThreads, 2) dwconv3d_kernel(const T* __rest
                                                               const DwGeom g) {
     const DwCoord k = dw_coord(g, (int64_t)blockIdx.x * kDwThreads + threadIdx.x);
     if (!k.live) return;
-    const bool wpair = g.C % 2 == 0;
+    const bool wpair = kPair;   // the host-side decision covers C even AND 8-byte aligned weight / bias pointers
     float2 w[27];
 #pragma unroll
     for (int t = 0; t < 27; ++t) w[t] = dw_ldw(weight + (int64_t)(kMirror ? 26 - t : t) * g.C + k.c, k.c, g.C, wpair);

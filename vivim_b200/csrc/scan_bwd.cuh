@@ -69,25 +69,57 @@ __device__ __forceinline__ float4 add4(float4 v, float2 lo, float2 hi) {
 template <typename T, bool kVec, int NB>
 struct BwdTileLoader {
     static constexpr int kPer = (NB * 8 + kBwdThreads - 1) / kBwdThreads;
+    static constexpr int kQuads = kSeg * (NB / 4);
+    static constexpr int kPerQ = (kQuads + kBwdThreads - 1) / kBwdThreads;
     Raw8<T, kVec> raw[kPer];
-    __device__ __forceinline__ void load(const T* __restrict__ base, int64_t ns, int N, int t0, int L) {
+    StateQuad<T> quad[kPerQ];
+    bool rows;   // see StateTileLoader (scan_seq.cuh): `rows` = (.., N, L) layout walked left to right, else (position, 4 states) items
+    __device__ __forceinline__ void load(const T* __restrict__ base, int64_t ns, int64_t ls, int N, int t0, const Trav& tr) {
+        rows = ls <= 1 && tr.mode == VV_DIR_FWD;
+        if (rows) {
 #pragma unroll
-        for (int j = 0; j < kPer; ++j) {
-            const int idx = threadIdx.x + j * kBwdThreads;
-            const int n = idx >> 3, tb = idx & 7;
-            raw[j].load(base + (n < N ? n : 0) * ns, (n < N && n < NB) ? t0 + tb * 8 : L, L);   // rows >= N read as 0
+            for (int j = 0; j < kPer; ++j) {
+                const int idx = threadIdx.x + j * kBwdThreads;
+                const int n = idx >> 3, tb = idx & 7;
+                raw[j].load(base + (n < N ? n : 0) * ns, (n < N && n < NB) ? t0 + tb * 8 : tr.L, tr.L);   // rows >= N read as 0
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < kPerQ; ++j) {
+                const int idx = threadIdx.x + j * kBwdThreads;
+                const int n4 = idx / kSeg, pos = idx - n4 * kSeg;   // position fastest: 2-way bank conflicts on the transposed stores
+                quad[j].load(base, ns, ls < 1 ? 1 : ls, N, n4 * 4, t0 + pos, idx < kQuads, tr);
+            }
         }
     }
     __device__ __forceinline__ void store(float4* __restrict__ tile) const {
+        if (rows) {
 #pragma unroll
-        for (int j = 0; j < kPer; ++j) {
-            const int idx = threadIdx.x + j * kBwdThreads;
-            const int n = idx >> 3, tb = idx & 7;
-            if (n < NB) {
-                float v[8];
-                raw[j].unpack(v);
-                tile[n * kBwdSlots + tb] = make_float4(v[0], v[1], v[2], v[3]);
-                tile[n * kBwdSlots + 8 + tb] = make_float4(v[4], v[5], v[6], v[7]);
+            for (int j = 0; j < kPer; ++j) {
+                const int idx = threadIdx.x + j * kBwdThreads;
+                const int n = idx >> 3, tb = idx & 7;
+                if (n < NB) {
+                    float v[8];
+                    raw[j].unpack(v);
+                    tile[n * kBwdSlots + tb] = make_float4(v[0], v[1], v[2], v[3]);
+                    tile[n * kBwdSlots + 8 + tb] = make_float4(v[4], v[5], v[6], v[7]);
+                }
+            }
+        } else {
+            float* tf = reinterpret_cast<float*>(tile);
+#pragma unroll
+            for (int j = 0; j < kPerQ; ++j) {
+                const int idx = threadIdx.x + j * kBwdThreads;
+                if (idx < kQuads) {
+                    const int n4 = idx / kSeg, pos = idx - n4 * kSeg;
+                    const int slot = (pos >> 3) + ((pos & 4) ? 8 : 0);       // float4 slot of the position inside a state row
+                    const float4 v = quad[j].unpack();
+                    float* dst = tf + (n4 * 4 * kBwdSlots + slot) * 4 + (pos & 3);
+                    dst[0] = v.x;
+                    dst[4 * kBwdSlots] = v.y;
+                    dst[8 * kBwdSlots] = v.z;
+                    dst[12 * kBwdSlots] = v.w;
+                }
             }
         }
     }
@@ -127,16 +159,18 @@ __global__ void __launch_bounds__(kBwdThreads, 4) seg_bwd_kernel(const vv_scan_a
     const int S = gridDim.x;
     const int t0s = seg * kSeg;
     const int t0 = live ? t0s + tb * 8 : L;   // dead channels read as padding
+    const Trav tr = group_trav(a, grp);       // t0 / t0s are TRAVERSAL positions of the direction block
+    const int dg = gate_row(a, d);
 
     // ---- every global load that does not depend on the preceding kernels, issued up front
     Raw8<T, kVec> r_dt, r_u, r_g, r_z;
-    r_dt.load(reinterpret_cast<const T*>(a.delta) + b * a.delta_bs + d * a.delta_ds, t0, L);
-    r_u.load(reinterpret_cast<const T*>(a.u) + b * a.u_bs + d * a.u_ds, t0, L);
-    r_g.load(reinterpret_cast<const T*>(a.dout) + b * a.dout_bs + d * a.dout_ds, t0, L);
-    if (a.z) r_z.load(reinterpret_cast<const T*>(a.z) + b * a.z_bs + d * a.z_ds, t0, L);
+    r_dt.load_trav(reinterpret_cast<const T*>(a.delta) + b * a.delta_bs + d * a.delta_ds, t0, tr);
+    r_u.load_trav(reinterpret_cast<const T*>(a.u) + b * a.u_bs + d * a.u_ds, t0, tr);
+    r_g.load_trav(reinterpret_cast<const T*>(a.dout) + b * a.dout_bs + dg * a.dout_ds, t0, tr);
+    if (a.z) r_z.load_trav(reinterpret_cast<const T*>(a.z) + b * a.z_bs + dg * a.z_ds, t0, tr);
     BwdTileLoader<T, kVec, NB> lB, lC;
-    lB.load(reinterpret_cast<const T*>(a.Bm) + b * a.B_bs + grp * a.B_gs, a.B_ns, N, t0s, L);
-    lC.load(reinterpret_cast<const T*>(a.Cm) + b * a.C_bs + grp * a.C_gs, a.C_ns, N, t0s, L);
+    lB.load(reinterpret_cast<const T*>(a.Bm) + b * a.B_bs + grp * a.B_gs, a.B_ns, a.B_ls, N, t0s, tr);
+    lC.load(reinterpret_cast<const T*>(a.Cm) + b * a.C_bs + grp * a.C_gs, a.C_ns, a.C_ls, N, t0s, tr);
     const float bias = a.delta_bias ? a.delta_bias[d] : 0.f;
     const float Dv = a.D ? a.D[d] : 0.f;
     const bool sp = a.delta_softplus != 0;
@@ -363,12 +397,12 @@ __global__ void __launch_bounds__(kBwdThreads, 4) seg_bwd_kernel(const vv_scan_a
             dD_loc = fmaf(gi, u[i], dD_loc);
         }
         if (live) {
-            store8<T, kVec>(reinterpret_cast<T*>(a.du) + b * a.du_bs + d * a.du_ds, t0, L, du_o);
-            store8<T, kVec>(reinterpret_cast<T*>(a.ddelta) + b * a.ddelta_bs + d * a.ddelta_ds, t0, L, ddt_o);
+            store8_trav<T, kVec>(reinterpret_cast<T*>(a.du) + b * a.du_bs + d * a.du_ds, t0, tr, du_o);
+            store8_trav<T, kVec>(reinterpret_cast<T*>(a.ddelta) + b * a.ddelta_bs + d * a.ddelta_ds, t0, tr, ddt_o);
             if (a.z) {
 #pragma unroll
                 for (int i = 0; i < 8; ++i) dzf[i] *= fmaf(Dv, u[i], (i & 1) ? y2[i >> 1].y : y2[i >> 1].x);
-                store8<T, kVec>(reinterpret_cast<T*>(a.dz) + b * a.dz_bs + d * a.dz_ds, t0, L, dzf);
+                store8_trav<T, kVec>(reinterpret_cast<T*>(a.dz) + b * a.dz_bs + d * a.dz_ds, t0, tr, dzf);
             }
         }
 #pragma unroll
@@ -443,6 +477,39 @@ __global__ void __launch_bounds__(256) cast_bc_kernel(const float* __restrict__ 
         store8_vec<T>(dst + i, v);
     } else {
         for (int64_t k = i; k < n && k < i + 8; ++k) dst[k] = from_f32<T>(src[k]);
+    }
+}
+
+// The same cast for any output layout and traversal order: the fp32 accumulators are (B,G,N,L) in TRAVERSAL order, the
+// destination is indexed by MEMORY position with arbitrary strides -- e.g. the B / C column blocks of dx_dbl
+// (B*L, R+2N), which the reference fills through `rearrange(dB, "b 1 dstate l -> (b l) dstate")` and a slice copy
+// (selective_scan_interface.py:255-271).  One CTA per (64-position segment, group, batch): the accumulator rows are read
+// along L (coalesced), transposed through shared memory and written with the state index fastest.
+constexpr int kCastThreads = 256;
+template <typename T>
+__global__ void __launch_bounds__(kCastThreads) cast_bc_strided_kernel(const vv_scan_args a) {
+    __shared__ float tile[2][kMaxState][kSeg + 1];
+    pdl_wait();
+    const int N = a.dstate, L = a.seqlen;
+    const int seg = blockIdx.x, g = blockIdx.y, b = blockIdx.z;
+    const int t0 = seg * kSeg;
+    const Trav tr = group_trav(a, g);
+    const int64_t acc_base = (((int64_t)b * a.ngroups + g) * N) * L;
+    for (int idx = threadIdx.x; idx < 2 * N * kSeg; idx += kCastThreads) {
+        const int which = idx / (N * kSeg), rem = idx - which * N * kSeg;
+        const int n = rem / kSeg, j = rem - n * kSeg;
+        const float* src = which ? a.dC : a.dB;
+        tile[which][n][j] = (t0 + j < L) ? src[acc_base + (int64_t)n * L + t0 + j] : 0.f;
+    }
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < 2 * N * kSeg; idx += kCastThreads) {
+        const int j = idx / (2 * N), rem = idx - j * 2 * N;
+        const int which = rem / N, n = rem - which * N;
+        if (t0 + j < L) {
+            const int64_t m = tr.mem(t0 + j);
+            if (which) reinterpret_cast<T*>(a.dC_io)[b * a.dCio_bs + g * a.dCio_gs + n * a.dCio_ns + m * a.dCio_ls] = from_f32<T>(tile[1][n][j]);
+            else reinterpret_cast<T*>(a.dB_io)[b * a.dBio_bs + g * a.dBio_gs + n * a.dBio_ns + m * a.dBio_ls] = from_f32<T>(tile[0][n][j]);
+        }
     }
 }
 

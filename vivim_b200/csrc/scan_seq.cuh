@@ -72,31 +72,101 @@ __device__ __forceinline__ void load_states(const float* __restrict__ p, float (
     }
 }
 
-// B or C of the segment: global (N rows, stride ns) -> fp32 tile[position][NB] (states >= N are 0).
-// Split in two so that the loads can be issued early and consumed late.
+// Four consecutive states of one token, from any (state stride, sequence stride) layout: the (B,G,N,L) tensors of the
+// reference op (ns = L, ls = 1) or rows of x_proj's GEMM output x_dbl (ns = 1, ls = R+2N; reference:
+// selective_scan_interface.py:187-207 transposes those into (B,1,N,L) first).  Kept packed until store time.
+template <typename T>
+struct StateQuad {                    // 16-bit element types
+    uint32_t w[2];
+    __device__ __forceinline__ void load(const T* __restrict__ base, int64_t ns, int64_t ls, int N, int n0, int pos,
+                                         bool valid, const Trav& tr) {
+        w[0] = w[1] = 0u;
+        if (!valid || pos >= tr.L || n0 >= N) return;
+        const T* p = base + (int64_t)tr.mem(pos) * ls + (int64_t)n0 * ns;
+        if (ns == 1 && n0 + 4 <= N && reinterpret_cast<uintptr_t>(p) % 8 == 0) {
+            const uint2 v = __ldg(reinterpret_cast<const uint2*>(p));
+            w[0] = v.x; w[1] = v.y;
+            return;
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            if (n0 + k < N)
+                w[k >> 1] |= (uint32_t)__ldg(reinterpret_cast<const unsigned short*>(p + k * ns)) << (16 * (k & 1));
+    }
+    __device__ __forceinline__ float4 unpack() const {
+        const float2 a = unpack_pair<T>(w[0]), b = unpack_pair<T>(w[1]);
+        return make_float4(a.x, a.y, b.x, b.y);
+    }
+};
+template <>
+struct StateQuad<float> {
+    float4 v;
+    __device__ __forceinline__ void load(const float* __restrict__ base, int64_t ns, int64_t ls, int N, int n0, int pos,
+                                         bool valid, const Trav& tr) {
+        v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (!valid || pos >= tr.L || n0 >= N) return;
+        const float* p = base + (int64_t)tr.mem(pos) * ls + (int64_t)n0 * ns;
+        if (ns == 1 && n0 + 4 <= N && reinterpret_cast<uintptr_t>(p) % 16 == 0) {
+            v = __ldg(reinterpret_cast<const float4*>(p));
+            return;
+        }
+        if (n0 + 0 < N) v.x = __ldg(p);
+        if (n0 + 1 < N) v.y = __ldg(p + ns);
+        if (n0 + 2 < N) v.z = __ldg(p + 2 * ns);
+        if (n0 + 3 < N) v.w = __ldg(p + 3 * ns);
+    }
+    __device__ __forceinline__ float4 unpack() const { return v; }
+};
+
+// B or C of the segment -> fp32 tile[position][NB] (states >= N are 0).  Split in two so that the loads can be issued
+// early and consumed late.  Two routes, chosen per CTA: `rows` = the (.., N, L) layout walked left to right (one 128-bit
+// load covers 8 positions of a state row), `quads` = anything else (position-major rows, reversed or frame-interleaved
+// traversal): (position, 4 states) items, state index fastest so that a row of x_dbl is read by adjacent lanes.
 template <typename T, bool kVec, int NB>
 struct StateTileLoader {
     static constexpr int kChunks = kSeg / 8;
     static constexpr int kPer = (NB * kChunks + kSegThreads - 1) / kSegThreads;
+    static constexpr int kQuads = kSeg * (NB / 4);
+    static constexpr int kPerQ = (kQuads + kSegThreads - 1) / kSegThreads;
     Raw8<T, kVec> raw[kPer];
-    __device__ __forceinline__ void load(const T* __restrict__ base, int64_t ns, int N, int t0, int L) {
+    StateQuad<T> quad[kPerQ];
+    bool rows;
+    __device__ __forceinline__ void load(const T* __restrict__ base, int64_t ns, int64_t ls, int N, int t0, const Trav& tr) {
+        rows = ls <= 1 && tr.mode == VV_DIR_FWD;
+        if (rows) {
 #pragma unroll
-        for (int j = 0; j < kPer; ++j) {
-            const int idx = threadIdx.x + j * kSegThreads;
-            const int c = idx / NB, n = idx - c * NB;   // n fastest: the transposed shared stores spread over banks
-            raw[j].load(base + (n < N ? n : 0) * ns, (n < N && c < kChunks) ? t0 + c * 8 : L, L);
+            for (int j = 0; j < kPer; ++j) {
+                const int idx = threadIdx.x + j * kSegThreads;
+                const int c = idx / NB, n = idx - c * NB;   // n fastest: the transposed shared stores spread over banks
+                raw[j].load(base + (n < N ? n : 0) * ns, (n < N && c < kChunks) ? t0 + c * 8 : tr.L, tr.L);
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < kPerQ; ++j) {
+                const int idx = threadIdx.x + j * kSegThreads;
+                const int pos = idx / (NB / 4), n4 = idx - pos * (NB / 4);
+                quad[j].load(base, ns, ls < 1 ? 1 : ls, N, n4 * 4, t0 + pos, idx < kQuads, tr);
+            }
         }
     }
     __device__ __forceinline__ void store(float* __restrict__ tile) const {
+        if (rows) {
 #pragma unroll
-        for (int j = 0; j < kPer; ++j) {
-            const int idx = threadIdx.x + j * kSegThreads;
-            const int c = idx / NB, n = idx - c * NB;
-            if (c < kChunks) {
-                float v[8];
-                raw[j].unpack(v);
+            for (int j = 0; j < kPer; ++j) {
+                const int idx = threadIdx.x + j * kSegThreads;
+                const int c = idx / NB, n = idx - c * NB;
+                if (c < kChunks) {
+                    float v[8];
+                    raw[j].unpack(v);
 #pragma unroll
-                for (int i = 0; i < 8; ++i) tile[(c * 8 + i) * NB + n] = v[i];
+                    for (int i = 0; i < 8; ++i) tile[(c * 8 + i) * NB + n] = v[i];
+                }
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < kPerQ; ++j) {
+                const int idx = threadIdx.x + j * kSegThreads;
+                if (idx < kQuads) reinterpret_cast<float4*>(tile)[idx] = quad[j].unpack();   // tile[pos * NB + n4 * 4]
             }
         }
     }
@@ -104,7 +174,22 @@ struct StateTileLoader {
 
 struct SegCoord {
     int b, g, d0, nrows, seg, t0;   // d0: first channel of the CTA, nrows: valid channels in the CTA
+    Trav tr;                        // traversal order of the CTA's direction block
 };
+
+// traversal order of group g (groups are split evenly over the direction blocks)
+__device__ __forceinline__ Trav group_trav(const vv_scan_args& a, int g) {
+    Trav tr;
+    const int ndirs = a.ndirs > 1 ? a.ndirs : 1;
+    tr.mode = a.dir_mode[g / (a.ngroups / ndirs)];
+    tr.L = a.seqlen;
+    tr.nf = a.nframes > 0 ? a.nframes : 1;
+    tr.hw = a.seqlen / tr.nf;
+    return tr;
+}
+
+// channel row of the tensors shared by the direction blocks (z, dout)
+__device__ __forceinline__ int gate_row(const vv_scan_args& a, int d) { return a.gate_rows > 0 ? d % a.gate_rows : d; }
 
 __device__ __forceinline__ SegCoord seg_coord(const vv_scan_args& a) {
     SegCoord c;
@@ -117,6 +202,7 @@ __device__ __forceinline__ SegCoord seg_coord(const vv_scan_args& a) {
     const int off = (blockIdx.y - c.g * blocks_per_group) * kSegRows;
     c.d0 = c.g * dpg + off;
     c.nrows = min(kSegRows, dpg - off);
+    c.tr = group_trav(a, c.g);
     return c;
 }
 
@@ -130,13 +216,13 @@ struct SegPrepass {
     Raw8<T, kVec> r_dt[2], r_cf[2], r_z[2];
     int t[2];
     __device__ __forceinline__ void load(const T* __restrict__ g_dt, const T* __restrict__ g_cf, const T* __restrict__ g_z,
-                                         bool live, int q, int t0, int L) {
+                                         bool live, int q, int t0, const Trav& tr) {
 #pragma unroll
         for (int k = 0; k < 2; ++k) {
-            t[k] = live ? t0 + (q + 4 * k) * 8 : L;   // dead rows read as padding
-            r_dt[k].load(g_dt, t[k], L);
-            r_cf[k].load(g_cf, t[k], L);
-            if (g_z) r_z[k].load(g_z, t[k], L);
+            t[k] = live ? t0 + (q + 4 * k) * 8 : tr.L;   // dead rows read as padding
+            r_dt[k].load_trav(g_dt, t[k], tr);
+            r_cf[k].load_trav(g_cf, t[k], tr);
+            if (g_z) r_z[k].load_trav(g_z, t[k], tr);
         }
     }
     __device__ __forceinline__ void finish(bool has_z, unsigned char* __restrict__ f_dt, unsigned char* __restrict__ f_cf,
@@ -178,8 +264,10 @@ struct SegPrepass {
 //               e_t = a_t r_t is the adjoint of h_t pushed through its own decay: its segment
 //               aggregate has the SAME decay product as the forward one and needs nothing from
 //               the neighbouring segment.
+// Register budget: the 128-bit variants with <= 16 states fit 56 registers (9 CTAs / SM: one wave at the B = 1 stage-1
+// shape); the element-wise, fp32 and 32-state variants would spill there and get 96.
 template <typename T, bool kVec, int NB, bool kRev>
-__global__ void __launch_bounds__(kSegThreads, 9) seg_agg_kernel(const vv_scan_args a) {
+__global__ void __launch_bounds__(kSegThreads, (kVec && NB <= 16 && sizeof(T) == 2) ? 9 : 5) seg_agg_kernel(const vv_scan_args a) {
     constexpr int NQ = NB / 4;
     extern __shared__ __align__(16) unsigned char smem[];
     const int L = a.seqlen, N = a.dstate;
@@ -187,11 +275,17 @@ __global__ void __launch_bounds__(kSegThreads, 9) seg_agg_kernel(const vv_scan_a
     unsigned char* f_dt = smem;
     unsigned char* f_cf = f_dt + kSegRows * kF32Pitch;
     float* t_m = reinterpret_cast<float*>(f_cf + kSegRows * kF32Pitch);
+    // FIRST kernel of vv_scan_fwd / vv_scan_bwd: its stream predecessor is whatever produced the caller's tensors
+    // (a GEMM, a conv, another scan) and may itself have released its dependents early, so nothing the caller provides
+    // -- inputs AND parameters -- is read before the predecessor has completed.  Only index arithmetic runs ahead.  The
+    // dependents (carry, main) are released after that point, so their own pre-wait loads are safe as well.
+    pdl_wait();
     pdl_trigger();
 
     const int r = threadIdx.x >> 2, q = threadIdx.x & 3;
     const bool live = r < c.nrows;
     const int d = c.d0 + (live ? r : 0);
+    const int dg = gate_row(a, d);
     const float bias = a.delta_bias ? a.delta_bias[d] : 0.f;
     const bool sp = a.delta_softplus != 0;
     const T* g_dt = reinterpret_cast<const T*>(a.delta) + c.b * a.delta_bs + d * a.delta_ds;
@@ -199,12 +293,12 @@ __global__ void __launch_bounds__(kSegThreads, 9) seg_agg_kernel(const vv_scan_a
     SegPrepass<T, kVec, kRev ? 1 : 0> pre;
     StateTileLoader<T, kVec, NB> st;
     if (!kRev) {
-        pre.load(g_dt, reinterpret_cast<const T*>(a.u) + c.b * a.u_bs + d * a.u_ds, nullptr, live, q, c.t0, L);
-        st.load(reinterpret_cast<const T*>(a.Bm) + c.b * a.B_bs + c.g * a.B_gs, a.B_ns, N, c.t0, L);
+        pre.load(g_dt, reinterpret_cast<const T*>(a.u) + c.b * a.u_bs + d * a.u_ds, nullptr, live, q, c.t0, c.tr);
+        st.load(reinterpret_cast<const T*>(a.Bm) + c.b * a.B_bs + c.g * a.B_gs, a.B_ns, a.B_ls, N, c.t0, c.tr);
     } else {
-        pre.load(g_dt, reinterpret_cast<const T*>(a.dout) + c.b * a.dout_bs + d * a.dout_ds,
-                 a.z ? reinterpret_cast<const T*>(a.z) + c.b * a.z_bs + d * a.z_ds : nullptr, live, q, c.t0, L);
-        st.load(reinterpret_cast<const T*>(a.Cm) + c.b * a.C_bs + c.g * a.C_gs, a.C_ns, N, c.t0, L);
+        pre.load(g_dt, reinterpret_cast<const T*>(a.dout) + c.b * a.dout_bs + dg * a.dout_ds,
+                 a.z ? reinterpret_cast<const T*>(a.z) + c.b * a.z_bs + dg * a.z_ds : nullptr, live, q, c.t0, c.tr);
+        st.load(reinterpret_cast<const T*>(a.Cm) + c.b * a.C_bs + c.g * a.C_gs, a.C_ns, a.C_ls, N, c.t0, c.tr);
     }
     float A2[NQ], h[NQ];
 #pragma unroll
@@ -245,10 +339,6 @@ __global__ void __launch_bounds__(kSegThreads, 9) seg_agg_kernel(const vv_scan_a
     }
     const int S = gridDim.x;
     float2* out = reinterpret_cast<float2*>(a.agg) + (((int64_t)c.b * a.dim + d) * S + c.seg) * N;
-    // Launched as a programmatic dependent: everything above only reads this call's inputs and may overlap the
-    // tail of the preceding kernel; `agg` may still be read by it (a carry pass of an earlier call), so the
-    // stores wait for its completion.
-    pdl_wait();
     if (kRev && a.zero_accumulators) {
         // The backward's fp32 accumulators are zero-filled here, by the first kernel of vv_scan_bwd and after the
         // dependency wait (whatever used the buffers before is complete), instead of by a memset launch of the caller:
@@ -384,9 +474,9 @@ __global__ void __launch_bounds__(kSegThreads) seg_fwd_kernel(const vv_scan_args
     StateTileLoader<T, kVec, NB> stB, stC;
     pre.load(reinterpret_cast<const T*>(a.delta) + c.b * a.delta_bs + d * a.delta_ds,
              reinterpret_cast<const T*>(a.u) + c.b * a.u_bs + d * a.u_ds,
-             a.z ? reinterpret_cast<const T*>(a.z) + c.b * a.z_bs + d * a.z_ds : nullptr, live, q, c.t0, L);
-    stB.load(reinterpret_cast<const T*>(a.Bm) + c.b * a.B_bs + c.g * a.B_gs, a.B_ns, N, c.t0, L);
-    stC.load(reinterpret_cast<const T*>(a.Cm) + c.b * a.C_bs + c.g * a.C_gs, a.C_ns, N, c.t0, L);
+             a.z ? reinterpret_cast<const T*>(a.z) + c.b * a.z_bs + gate_row(a, d) * a.z_ds : nullptr, live, q, c.t0, c.tr);
+    stB.load(reinterpret_cast<const T*>(a.Bm) + c.b * a.B_bs + c.g * a.B_gs, a.B_ns, a.B_ls, N, c.t0, c.tr);
+    stC.load(reinterpret_cast<const T*>(a.Cm) + c.b * a.C_bs + c.g * a.C_gs, a.C_ns, a.C_ls, N, c.t0, c.tr);
     float A2[NQ], h[NQ];
 #pragma unroll
     for (int k = 0; k < NQ; ++k) {
@@ -480,11 +570,11 @@ __global__ void __launch_bounds__(kSegThreads) seg_fwd_kernel(const vv_scan_args
             float v[8];
             if (a.out) {
                 tile_read8<T>(my_z, ch, v);
-                store8<T, kVec>(reinterpret_cast<T*>(a.out) + c.b * a.out_bs + d * a.out_ds, c.t0 + ch * 8, L, v);
+                store8_trav<T, kVec>(reinterpret_cast<T*>(a.out) + c.b * a.out_bs + d * a.out_ds, c.t0 + ch * 8, c.tr, v);
             }
             if (a.z) {
                 tile_read8<T>(my_u, ch, v);
-                store8<T, kVec>(reinterpret_cast<T*>(a.out_z) + c.b * a.outz_bs + d * a.outz_ds, c.t0 + ch * 8, L, v);
+                store8_trav<T, kVec>(reinterpret_cast<T*>(a.out_z) + c.b * a.outz_bs + d * a.outz_ds, c.t0 + ch * 8, c.tr, v);
             }
         }
     }

@@ -9,6 +9,7 @@
 
 #include "../../include/vivim_b200.h"
 #include "conv1d.cuh"
+#include "conv1d_dirs.cuh"
 #include "dwconv3d.cuh"
 #include "scan_bwd.cuh"
 #include "scan_seq.cuh"
@@ -17,7 +18,6 @@ namespace {
 
 thread_local char g_err[512] = "";
 thread_local int g_launches = 0;
-thread_local int g_pass_mask = 15;
 
 int fail(int code, const char* fmt, ...) {
     va_list ap;
@@ -47,9 +47,35 @@ int check_launch(const char* what) {
     return VV_OK;
 }
 
+template <typename K>
+int set_smem(K kernel, size_t bytes) {
+    if (bytes <= 48 * 1024) return VV_OK;
+    const cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (e != cudaSuccess) return fail((int)e, "cudaFuncSetAttribute(%zu B): %s", bytes, cudaGetErrorString(e));
+    return VV_OK;
+}
+
 int env_int(const char* name, int dflt) {
     const char* v = getenv(name);
     return (v && *v) ? atoi(v) : dflt;
+}
+
+// process-wide test switch, read from the environment once (vv_debug_force_scalar_io changes it)
+int& force_scalar_io() {
+    static int on = env_int("VV_FORCE_SCALAR_IO", 0);
+    return on;
+}
+
+// SM count of the current device (queried once per device)
+int sm_count() {
+    static int cached[64] = {0};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+    if (cached[dev] == 0) {
+        int n = 0;
+        cached[dev] = (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0) ? n : 148;
+    }
+    return cached[dev];
 }
 
 // ---------------------------------------------------------------- conv1d dispatch
@@ -85,12 +111,80 @@ int launch_conv(const vv_conv1d_args* a, void* stream) {
     bool vec = a->seqlen % 8 == 0 && vec_ok(a->x, es, {a->x_bs, a->x_ds});
     if (kBwd) vec = vec && vec_ok(a->dout, es, {a->dout_bs, a->dout_ds}) && vec_ok(a->dx, es, {a->dx_bs, a->dx_ds});
     else vec = vec && vec_ok(a->out, es, {a->out_bs, a->out_ds});
-    if (env_int("VV_FORCE_SCALAR_IO", 0)) vec = false;
+    if (force_scalar_io()) vec = false;
+    if ((int64_t)a->batch * a->dim > 2147483647ll || (a->seqlen + vv::kConvTile - 1) / vv::kConvTile > 65535)
+        return fail(VV_ERR_UNSUPPORTED, "conv1d: batch * dim > 2^31 - 1 or seqlen > 65535 * %d", vv::kConvTile);
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     switch (a->io_dtype) {
         case VV_F32: return launch_conv_t<float, kBwd>(*a, vec, st);
         case VV_F16: return launch_conv_t<__half, kBwd>(*a, vec, st);
         default: return launch_conv_t<__nv_bfloat16, kBwd>(*a, vec, st);
+    }
+}
+
+// ---------------------------------------------------------------- conv1d of several directions
+template <typename T, bool kBwd>
+int launch_conv_dirs_t(const vv_conv1d_dirs_args& a, bool vec, int pt, cudaStream_t st) {
+    const int nf = a.nframes > 0 ? a.nframes : 1, hw = a.seqlen / nf;
+    const dim3 grid((unsigned)((int64_t)a.batch * a.dim), (unsigned)((hw + pt - 1) / pt));
+    const size_t tile = (size_t)nf * (pt + 2 * vv::kDirsHalo) * sizeof(float);
+    const size_t smem = kBwd ? (a.ndirs + 1) * tile + (vv::kDirsThreads / 32) * VV_MAX_DIRS * 5 * sizeof(float) : tile;
+    int rc;
+#define VV_DIRS_LAUNCH(SILU, VEC)                                                                                     \
+    do {                                                                                                              \
+        if (kBwd) {                                                                                                   \
+            if ((rc = set_smem(vv::conv1d_dirs_bwd_kernel<T, SILU, VEC>, smem)) != VV_OK) return rc;                  \
+            vv::conv1d_dirs_bwd_kernel<T, SILU, VEC><<<grid, vv::kDirsThreads, smem, st>>>(a, pt);                    \
+        } else {                                                                                                      \
+            if ((rc = set_smem(vv::conv1d_dirs_fwd_kernel<T, SILU, VEC>, smem)) != VV_OK) return rc;                  \
+            vv::conv1d_dirs_fwd_kernel<T, SILU, VEC><<<grid, vv::kDirsThreads, smem, st>>>(a, pt);                    \
+        }                                                                                                             \
+    } while (0)
+    if (a.silu) { if (vec) VV_DIRS_LAUNCH(true, true); else VV_DIRS_LAUNCH(true, false); }
+    else        { if (vec) VV_DIRS_LAUNCH(false, true); else VV_DIRS_LAUNCH(false, false); }
+#undef VV_DIRS_LAUNCH
+    return check_launch(kBwd ? "conv1d_dirs_bwd_kernel" : "conv1d_dirs_fwd_kernel");
+}
+
+template <bool kBwd>
+int launch_conv_dirs(const vv_conv1d_dirs_args* a, void* stream) {
+    g_launches = 0;
+    if (!a) return fail(VV_ERR_BAD_ARG, "conv1d_dirs: null args");
+    if (!a->x || !a->weight) return fail(VV_ERR_BAD_ARG, "conv1d_dirs: x and weight are required");
+    if (!kBwd && !a->out) return fail(VV_ERR_BAD_ARG, "conv1d_dirs_fwd: out is required");
+    if (kBwd && (!a->dout || !a->dx || !a->dweight)) return fail(VV_ERR_BAD_ARG, "conv1d_dirs_bwd: dout, dx, dweight are required");
+    if (kBwd && a->bias && !a->dbias) return fail(VV_ERR_BAD_ARG, "conv1d_dirs_bwd: dbias is required when bias is given");
+    if (a->batch <= 0 || a->dim <= 0 || a->seqlen <= 0) return fail(VV_ERR_BAD_ARG, "conv1d_dirs: sizes must be positive");
+    if (!valid_dtype(a->io_dtype)) return fail(VV_ERR_BAD_ARG, "conv1d_dirs: dtype must be fp32, fp16 or bf16");
+    if (a->width < 2 || a->width > 4) return fail(VV_ERR_UNSUPPORTED, "causal_conv1d only supports width between 2 and 4");
+    if (a->ndirs < 1 || a->ndirs > VV_MAX_DIRS) return fail(VV_ERR_BAD_ARG, "conv1d_dirs: ndirs must be in [1, %d]", VV_MAX_DIRS);
+    bool frames = false;
+    for (int k = 0; k < a->ndirs; ++k) {
+        const int m = a->dir_mode[k];
+        if (m != VV_DIR_FWD && m != VV_DIR_REV && m != VV_DIR_FRAMES) return fail(VV_ERR_BAD_ARG, "conv1d_dirs: bad dir_mode[%d]", k);
+        frames = frames || m == VV_DIR_FRAMES;
+    }
+    vv_conv1d_dirs_args b = *a;
+    if (!frames) b.nframes = 1;       // without a frame-interleaved direction the row is one run of L tokens
+    if (b.nframes <= 0 || b.seqlen % b.nframes != 0)
+        return fail(VV_ERR_BAD_ARG, "conv1d_dirs: VV_DIR_FRAMES needs nframes > 0 dividing seqlen (nframes %d, seqlen %d)", b.nframes, b.seqlen);
+    if (b.nframes > vv::kDirsMaxFrames) return fail(VV_ERR_UNSUPPORTED, "conv1d_dirs: nframes > %d", vv::kDirsMaxFrames);
+    const int es = elem_size(a->io_dtype);
+    if (!elem_aligned(a->x, es) || !elem_aligned(a->out, es) || !elem_aligned(a->dout, es) || !elem_aligned(a->dx, es))
+        return fail(VV_ERR_ALIGN, "conv1d_dirs: tensor not aligned to its element size");
+    const int nf = b.nframes, hw = b.seqlen / nf;
+    // pixels per CTA: about 1280 tokens of every direction, a multiple of the thread count
+    const int pt = std::max(128, std::min(1024, (1280 / nf) / 128 * 128));
+    if ((int64_t)a->batch * a->dim > 2147483647ll || (hw + pt - 1) / pt > 65535)
+        return fail(VV_ERR_UNSUPPORTED, "conv1d_dirs: grid too large");
+    bool vec = hw % 8 == 0 && vec_ok(a->x, es, {a->x_bs, a->x_ds});
+    if (kBwd) vec = vec && vec_ok(a->dout, es, {a->dout_bs, a->dout_ds});
+    if (force_scalar_io()) vec = false;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    switch (a->io_dtype) {
+        case VV_F32: return launch_conv_dirs_t<float, kBwd>(b, vec, pt, st);
+        case VV_F16: return launch_conv_dirs_t<__half, kBwd>(b, vec, pt, st);
+        default: return launch_conv_dirs_t<__nv_bfloat16, kBwd>(b, vec, pt, st);
     }
 }
 
@@ -101,7 +195,8 @@ int launch_dw_t(const vv_dwconv3d_args& a, cudaStream_t st) {
     const size_t pair_bytes = 2 * sizeof(T);
     auto aligned = [&](const void* p) { return p == nullptr || reinterpret_cast<uintptr_t>(p) % pair_bytes == 0; };
     const bool pair = a.channels % 2 == 0 && aligned(a.x) && aligned(a.out) && aligned(a.dout) && aligned(a.dx) &&
-                      reinterpret_cast<uintptr_t>(a.weight) % 8 == 0 && !env_int("VV_FORCE_SCALAR_IO", 0);
+                      reinterpret_cast<uintptr_t>(a.weight) % 8 == 0 && reinterpret_cast<uintptr_t>(a.bias) % 8 == 0 &&
+                      !force_scalar_io();
     const int cp = (a.channels + 1) / 2, xt = (a.width + vv::kDwX - 1) / vv::kDwX;
     const int64_t ncols = (int64_t)a.batch * a.height * xt;
     const unsigned blocks = (unsigned)((ncols * cp + vv::kDwThreads - 1) / vv::kDwThreads);
@@ -124,7 +219,7 @@ int launch_dw_t(const vv_dwconv3d_args& a, cudaStream_t st) {
 #undef VV_DW_STENCIL
     if (a.dweight) {
         const unsigned gx = (unsigned)((a.channels + 63) / 64);
-        int64_t gy = (4 * 148 + gx - 1) / gx;                       // ~4 CTAs of 256 threads per SM over the whole grid
+        int64_t gy = (4 * sm_count() + gx - 1) / gx;                // ~4 CTAs of 256 threads per SM over the whole grid
         gy = std::max<int64_t>(1, std::min<int64_t>(gy, (ncols + vv::kDwCols - 1) / vv::kDwCols));
         const dim3 grid(gx, (unsigned)gy), block(32, vv::kDwCols);
         if (pair) vv::dwconv3d_wgrad_kernel<T, true><<<grid, block, 0, st>>>(
@@ -209,17 +304,55 @@ int check_scan_common(const vv_scan_args* a, bool bwd) {
         if (a->delta_bias && !a->ddelta_bias) return fail(VV_ERR_BAD_ARG, "scan_bwd: ddelta_bias is required when delta_bias is given");
     }
     const int es = elem_size(a->io_dtype);
-    const void* ptrs[] = {a->u, a->delta, a->Bm, a->Cm, a->z, a->out, a->out_z, a->dout, a->du, a->ddelta, a->dz};
+    const void* ptrs[] = {a->u, a->delta, a->Bm, a->Cm, a->z, a->out, a->out_z, a->dout, a->du, a->ddelta, a->dz,
+                          a->dB_io, a->dC_io};
     for (const void* p : ptrs)
         if (!elem_aligned(p, es)) return fail(VV_ERR_ALIGN, "scan: tensor not aligned to its element size");
+    // directions
+    if (a->ndirs < 0 || a->ndirs > VV_MAX_DIRS) return fail(VV_ERR_BAD_ARG, "scan: ndirs must be in [0, %d]", VV_MAX_DIRS);
+    const int ndirs = a->ndirs > 1 ? a->ndirs : 1;
+    if (a->ngroups % ndirs != 0 || a->dim % ndirs != 0)
+        return fail(VV_ERR_BAD_ARG, "scan: ndirs must divide ngroups and dim");
+    for (int k = 0; k < ndirs; ++k) {
+        const int m = a->dir_mode[k];
+        if (m != VV_DIR_FWD && m != VV_DIR_REV && m != VV_DIR_FRAMES) return fail(VV_ERR_BAD_ARG, "scan: bad dir_mode[%d]", k);
+        if (m == VV_DIR_FRAMES && (a->nframes <= 0 || a->seqlen % a->nframes != 0))
+            return fail(VV_ERR_BAD_ARG, "scan: VV_DIR_FRAMES needs nframes > 0 dividing seqlen (nframes %d, seqlen %d)",
+                        a->nframes, a->seqlen);
+    }
+    if (a->gate_rows < 0 || a->gate_rows > a->dim) return fail(VV_ERR_BAD_ARG, "scan: gate_rows must be in [0, dim]");
+    if (a->B_ls < 0 || a->C_ls < 0) return fail(VV_ERR_BAD_ARG, "scan: negative B / C sequence stride");
+    // grid limits: y = channel blocks of all groups, z = batch
+    const int64_t dpg = a->dim / a->ngroups;
+    if ((int64_t)a->ngroups * ((dpg + vv::kBwdRows - 1) / vv::kBwdRows) > 65535)
+        return fail(VV_ERR_UNSUPPORTED, "scan: more than 65535 channel blocks (dim %d, ngroups %d)", a->dim, a->ngroups);
     return VV_OK;
+}
+
+bool all_forward(const vv_scan_args& a) {
+    const int ndirs = a.ndirs > 1 ? a.ndirs : 1;
+    for (int k = 0; k < ndirs; ++k)
+        if (a.dir_mode[k] != VV_DIR_FWD) return false;
+    return true;
+}
+
+// dB_io / dC_io are plain (B,G,N,L) contiguous tensors filled left to right: the flat cast kernel serves them
+bool bc_io_flat(const vv_scan_args& a) {
+    const int64_t N = a.dstate, L = a.seqlen, G = a.ngroups;
+    auto flat = [&](int64_t bs, int64_t gs, int64_t ns, int64_t ls) {
+        return (bs == 0 && gs == 0 && ns == 0 && ls == 0) || (bs == G * N * L && gs == N * L && ns == L && ls == 1);
+    };
+    return all_forward(a) && flat(a.dBio_bs, a.dBio_gs, a.dBio_ns, a.dBio_ls) && flat(a.dCio_bs, a.dCio_gs, a.dCio_ns, a.dCio_ls);
 }
 
 bool scan_vec_ok(const vv_scan_args& a, bool bwd) {
     const int es = elem_size(a.io_dtype);
     bool v = a.seqlen % 8 == 0;
     v = v && vec_ok(a.u, es, {a.u_bs, a.u_ds}) && vec_ok(a.delta, es, {a.delta_bs, a.delta_ds});
-    v = v && vec_ok(a.Bm, es, {a.B_bs, a.B_gs, a.B_ns}) && vec_ok(a.Cm, es, {a.C_bs, a.C_gs, a.C_ns});
+    // B / C: 128-bit row loads only in the (.., N, L) layout; position-major rows are read in (position, 4 states) items
+    // whose alignment is checked per item in the kernel
+    if (a.B_ls <= 1) v = v && vec_ok(a.Bm, es, {a.B_bs, a.B_gs, a.B_ns});
+    if (a.C_ls <= 1) v = v && vec_ok(a.Cm, es, {a.C_bs, a.C_gs, a.C_ns});
     v = v && vec_ok(a.z, es, {a.z_bs, a.z_ds});
     if (!bwd) {
         v = v && vec_ok(a.out, es, {a.out_bs, a.out_ds}) && vec_ok(a.out_z, es, {a.outz_bs, a.outz_ds});
@@ -228,17 +361,10 @@ bool scan_vec_ok(const vv_scan_args& a, bool bwd) {
         v = v && vec_ok(a.ddelta, es, {a.ddelta_bs, a.ddelta_ds}) && vec_ok(a.dz, es, {a.dz_bs, a.dz_ds});
         v = v && vec_ok(a.dB, 4, {}) && vec_ok(a.dC, 4, {});
     }
-    if (env_int("VV_FORCE_SCALAR_IO", 0)) v = false;
+    if (force_scalar_io()) v = false;
     return v;
 }
 
-template <typename K>
-int set_smem(K kernel, size_t bytes) {
-    if (bytes <= 48 * 1024) return VV_OK;
-    const cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
-    if (e != cudaSuccess) return fail((int)e, "cudaFuncSetAttribute(%zu B): %s", bytes, cudaGetErrorString(e));
-    return VV_OK;
-}
 
 // geometry of the segment kernels (scan_seq.cuh): 32 channels x one 64-position segment per CTA
 struct SegPlan {
@@ -246,6 +372,8 @@ struct SegPlan {
     int segs;
     dim3 grid;
 };
+
+int pass_mask(const vv_scan_args& a) { return a.pass_mask ? (a.pass_mask & 15) : 15; }
 
 SegPlan plan_seg(const vv_scan_args& a) {
     SegPlan p;
@@ -271,7 +399,7 @@ int launch_seg_fwd(const vv_scan_args& a, const SegPlan& p, cudaStream_t st) {
                         2 * (size_t)vv::kSegRows * vv::SegTile<T>::kPitch;
     int rc;
     if ((rc = set_smem(vv::seg_fwd_kernel<T, kVec, NB>, smem)) != VV_OK) return rc;
-    launch_kernel(vv::seg_fwd_kernel<T, kVec, NB>, p.grid, dim3(vv::kSegThreads), smem, st, use_pdl() && (g_pass_mask & 2), a);
+    launch_kernel(vv::seg_fwd_kernel<T, kVec, NB>, p.grid, dim3(vv::kSegThreads), smem, st, use_pdl() && (pass_mask(a) & 2), a);
     return check_launch("seg_fwd_kernel");
 }
 
@@ -282,7 +410,7 @@ int launch_seg_carry(const vv_scan_args& a, const SegPlan& p, cudaStream_t st) {
     const int chunks = std::max(1, std::min(vv::kCarryThreads / a.dstate, (p.segs + 3) / 4));
     const int rows_per_cta = std::max(1, vv::kCarryThreads / (chunks * a.dstate));
     launch_kernel(vv::seg_carry_kernel<kRev>, dim3((unsigned)((rows + rows_per_cta - 1) / rows_per_cta)),
-                  dim3(vv::kCarryThreads), 0, st, use_pdl() && (g_pass_mask & 1), reinterpret_cast<const float2*>(a.agg),
+                  dim3(vv::kCarryThreads), 0, st, use_pdl() && (pass_mask(a) & 1), reinterpret_cast<const float2*>(a.agg),
                   kRev ? a.radj : a.chk, kRev ? (float*)nullptr : a.last_state, p.segs, a.dstate, chunks, rows_per_cta, rows);
     return check_launch(kRev ? "seg_carry_kernel<rev>" : "seg_carry_kernel<fwd>");
 }
@@ -298,14 +426,14 @@ template <typename T, bool kVec>
 int scan_fwd_t(const vv_scan_args& a, cudaStream_t st) {
     const SegPlan p = plan_seg(a);
     int rc = VV_OK;
-    if (g_pass_mask & 1) {
+    if (pass_mask(a) & 1) {
         VV_NB_SWITCH(p.NB, rc = (launch_seg_agg<T, kVec, NB, false>(a, p, st)));
         if (rc != VV_OK) return rc;
     }
-    if (g_pass_mask & 2) {
+    if (pass_mask(a) & 2) {
         if ((rc = launch_seg_carry<false>(a, p, st)) != VV_OK) return rc;
     }
-    if (g_pass_mask & 4) {
+    if (pass_mask(a) & 4) {
         VV_NB_SWITCH(p.NB, rc = (launch_seg_fwd<T, kVec, NB>(a, p, st)));
         if (rc != VV_OK) return rc;
     }
@@ -316,31 +444,42 @@ template <typename T, bool kVec>
 int scan_bwd_t(const vv_scan_args& a, cudaStream_t st) {
     const SegPlan sp = plan_seg(a);
     int rc = VV_OK;
-    if (g_pass_mask & 1) {
+    if (pass_mask(a) & 1) {
         VV_NB_SWITCH(sp.NB, rc = (launch_seg_agg<T, kVec, NB, true>(a, sp, st)));
         if (rc != VV_OK) return rc;
     }
-    if (g_pass_mask & 2) {
+    if (pass_mask(a) & 2) {
         if ((rc = launch_seg_carry<true>(a, sp, st)) != VV_OK) return rc;
     }
-    if (g_pass_mask & 4) {
+    if (pass_mask(a) & 4) {
         const int dpg = a.dim / a.ngroups;
         const dim3 grid(sp.segs, a.ngroups * ((dpg + vv::kBwdRows - 1) / vv::kBwdRows), a.batch);
         VV_NB_SWITCH(sp.NB, {
             const size_t smem = vv::bwd_smem_bytes(NB);
             if ((rc = set_smem(vv::seg_bwd_kernel<T, kVec, NB>, smem)) != VV_OK) return rc;
             launch_kernel(vv::seg_bwd_kernel<T, kVec, NB>, grid, dim3(vv::kBwdThreads), smem, st,
-                          use_pdl() && (g_pass_mask & 2), a);
+                          use_pdl() && (pass_mask(a) & 2), a);
         });
         if ((rc = check_launch("seg_bwd_kernel")) != VV_OK) return rc;
     }
-    if ((g_pass_mask & 8) && a.dB_io != nullptr) {
-        {
+    if ((pass_mask(a) & 8) && a.dB_io != nullptr) {
+        if (bc_io_flat(a)) {
             const int64_t n = (int64_t)a.batch * a.ngroups * a.dstate * a.seqlen;
             const dim3 cgrid((unsigned)((n + 2047) / 2048), 2);
-            launch_kernel(vv::cast_bc_kernel<T>, cgrid, dim3(256), 0, st, use_pdl() && (g_pass_mask & 4), (const float*)a.dB, (const float*)a.dC,
+            launch_kernel(vv::cast_bc_kernel<T>, cgrid, dim3(256), 0, st, use_pdl() && (pass_mask(a) & 4), (const float*)a.dB, (const float*)a.dC,
                           reinterpret_cast<T*>(a.dB_io), reinterpret_cast<T*>(a.dC_io), n);
             if ((rc = check_launch("cast_bc_kernel")) != VV_OK) return rc;
+        } else {
+            vv_scan_args b = a;
+            if (b.dBio_bs == 0 && b.dBio_gs == 0 && b.dBio_ns == 0 && b.dBio_ls == 0) {
+                b.dBio_ls = 1; b.dBio_ns = a.seqlen; b.dBio_gs = (int64_t)a.dstate * a.seqlen; b.dBio_bs = b.dBio_gs * a.ngroups;
+            }
+            if (b.dCio_bs == 0 && b.dCio_gs == 0 && b.dCio_ns == 0 && b.dCio_ls == 0) {
+                b.dCio_ls = 1; b.dCio_ns = a.seqlen; b.dCio_gs = (int64_t)a.dstate * a.seqlen; b.dCio_bs = b.dCio_gs * a.ngroups;
+            }
+            launch_kernel(vv::cast_bc_strided_kernel<T>, dim3(sp.segs, a.ngroups, a.batch), dim3(vv::kCastThreads), 0, st,
+                          use_pdl() && (pass_mask(a) & 4), b);
+            if ((rc = check_launch("cast_bc_strided_kernel")) != VV_OK) return rc;
         }
     }
     return VV_OK;
@@ -373,15 +512,17 @@ extern "C" {
 int vv_version(void) { return VV_VERSION; }
 const char* vv_last_error(void) { return g_err; }
 int vv_last_launch_count(void) { return g_launches; }
-int vv_scan_set_pass_mask(int mask) {
-    const int prev = g_pass_mask;
-    g_pass_mask = mask & 15;
+int vv_debug_force_scalar_io(int on) {
+    const int prev = force_scalar_io();
+    force_scalar_io() = on != 0;
     return prev;
 }
 int vv_scan_num_segments(int seqlen) { return seqlen <= 0 ? 0 : (seqlen + VV_SCAN_SEGMENT - 1) / VV_SCAN_SEGMENT; }
 
 int vv_conv1d_fwd(const vv_conv1d_args* a, void* stream) { return launch_conv<false>(a, stream); }
 int vv_conv1d_bwd(const vv_conv1d_args* a, void* stream) { return launch_conv<true>(a, stream); }
+int vv_conv1d_dirs_fwd(const vv_conv1d_dirs_args* a, void* stream) { return launch_conv_dirs<false>(a, stream); }
+int vv_conv1d_dirs_bwd(const vv_conv1d_dirs_args* a, void* stream) { return launch_conv_dirs<true>(a, stream); }
 int vv_dwconv3d_fwd(const vv_dwconv3d_args* a, void* stream) { return launch_dw<false>(a, stream); }
 int vv_dwconv3d_bwd(const vv_dwconv3d_args* a, void* stream) { return launch_dw<true>(a, stream); }
 int vv_scan_fwd(const vv_scan_args* a, void* stream) { return launch_scan<false>(a, stream); }

@@ -15,9 +15,13 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from .causal_conv1d_interface import causal_conv1d_fn
+from .mamba_block import mamba_dirs_fn
 from .selective_scan_interface import mamba_inner_fn, mamba_inner_fn_no_out_proj, selective_scan_fn
 
 _DIRECTIONS = {"none": ("",), "v2": ("", "_b"), "v3": ("", "_b", "_s")}
+# traversal order of each parameter suffix (mamba_simple.py:217-260): as is, flipped, frame-interleaved
+_TRAVERSAL = {"": "fwd", "_b": "rev", "_s": "frames"}
+_MAX_DSTATE = 32   # state block of the sm_100a scan kernels (the reference serves up to 256)
 
 
 class Mamba(nn.Module):
@@ -28,6 +32,9 @@ class Mamba(nn.Module):
         super().__init__()
         if bimamba_type not in _DIRECTIONS:
             raise ValueError(f"bimamba_type must be one of {sorted(_DIRECTIONS)}")
+        if d_state > _MAX_DSTATE:
+            raise NotImplementedError(f"the B200 scan kernels serve d_state <= {_MAX_DSTATE} (got {d_state}); "
+                                      "the reference kernels serve up to 256 (INTEGRATION.md, 'Limits')")
         kw = {"device": device, "dtype": dtype}
         self.d_model, self.d_state, self.d_conv, self.expand = d_model, d_state, d_conv, expand
         self.d_inner = int(expand * d_model)
@@ -94,6 +101,13 @@ class Mamba(nn.Module):
         if inference_params is not None:
             raise NotImplementedError("autoregressive decoding (inference_params) is out of scope")
         batch, seqlen, _ = hidden_states.shape
+        sfxs = _DIRECTIONS[self.bimamba_type]
+        if self.use_fast_path and self.fuse_directions and len(sfxs) > 1 and hidden_states.is_cuda:
+            # every direction in one conv launch and one scan launch, no flip / interleave / transpose copies
+            return mamba_dirs_fn(hidden_states, self.in_proj.weight, self.in_proj.bias, self.out_proj.weight,
+                                 self.out_proj.bias, [self._direction_params(s) for s in sfxs],
+                                 tuple(_TRAVERSAL[s] for s in sfxs), self.nframes,
+                                 scale=1.0 / 3.0 if self.bimamba_type == "v3" else 1.0)
         # in_proj and the (b l d) -> (b d l) transpose in one GEMM (mamba_simple.py:204-210)
         xz = (self.in_proj.weight @ hidden_states.reshape(batch * seqlen, -1).t()) \
             .view(-1, batch, seqlen).transpose(0, 1)
@@ -108,6 +122,19 @@ class Mamba(nn.Module):
                 self.out_proj.weight, self.out_proj.bias, -torch.exp(self.A_log.float()), None, None,
                 self.D.float(), delta_bias=self.dt_proj.bias.float(), delta_softplus=True)
 
+        return self._forward_directions_unfused(xz, batch, seqlen)
+
+    fuse_directions = True   # class-level switch (tests compare the two routes)
+
+    def _direction_params(self, sfx):
+        conv, x_proj, dt_proj = (getattr(self, n + sfx) for n in ("conv1d", "x_proj", "dt_proj"))
+        return (conv.weight, conv.bias, x_proj.weight, dt_proj.weight,
+                -torch.exp(getattr(self, "A" + sfx + "_log").float()), getattr(self, "D" + sfx).float(),
+                dt_proj.bias.float())
+
+    def _forward_directions_unfused(self, xz, batch, seqlen):
+        """The reference's own data flow (mamba_simple.py:217-264): one mamba_inner_fn_no_out_proj per direction on
+        materialised flipped / frame-interleaved copies of xz.  Kept as the comparison route of the fused one."""
         y = self._scan_direction(xz, "")                                   # left to right
         y = y + self._scan_direction(xz.flip([-1]), "_b").flip([-1])      # right to left
         if self.bimamba_type == "v3":
