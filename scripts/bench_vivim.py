@@ -19,7 +19,7 @@ sys.path.insert(0, ROOT)
 import torch  # noqa: E402
 import torch.distributed as dist  # noqa: E402
 
-from vivim_b200.temporal_model import TemporalMambaBlock, Vivim  # noqa: E402
+from vivim_b200.temporal_model import RecallFocusedLoss, Vivim  # noqa: E402
 
 ap = argparse.ArgumentParser()
 ap.add_argument("--mode", choices=("train", "infer"), default="train")
@@ -67,8 +67,7 @@ if args.graph:
 if args.mode == "train" and args.full_graph:
     from vivim_b200.graphed import TrainStepGraph
     model.train()
-    tsg = TrainStepGraph(model, lambda logits, tgt: torch.nn.functional.cross_entropy(logits.float(), tgt),
-                         (clip,), (target,), autocast_dtype=torch.bfloat16)
+    tsg = TrainStepGraph(model, RecallFocusedLoss().to(dev), (clip,), (target,), autocast_dtype=torch.bfloat16)
     opt = torch.optim.AdamW(tsg.params, lr=1e-4, weight_decay=1e-2, fused=True, capturable=True)
 
     def step():
@@ -89,12 +88,13 @@ elif args.mode == "train":
         if args.bf16_allreduce:
             net.register_comm_hook(None, default_hooks.bf16_compress_hook)
     opt = torch.optim.AdamW([p for p in model.parameters() if p.requires_grad], lr=1e-4, weight_decay=1e-2)
+    loss_fn = RecallFocusedLoss().to(dev)
 
     def step():
         opt.zero_grad(set_to_none=True)
         with torch.autocast("cuda", dtype=torch.bfloat16):
             logits = net(clip)
-        loss = torch.nn.functional.cross_entropy(logits.float(), target)
+        loss = loss_fn(logits, target)
         loss.backward()
         opt.step()
         return loss

@@ -85,6 +85,50 @@ def selective_scan_fn(u, delta, A, B, C, D=None, z=None, delta_bias=None, delta_
     return SelectiveScanFn.apply(u, delta, A, B, C, D, z, delta_bias, delta_softplus, return_last_state)
 
 
+class SelectiveScanDirsFn(torch.autograd.Function):
+    """The scans of all directions of a Temporal Mamba block as one op (one launch chain instead of
+    ``len(dirs)`` calls of SelectiveScanFn on flipped / frame-interleaved copies, mamba_simple.py:217-260).
+
+    u, delta (B, nd*D, L): nd direction blocks of D channels; A (nd*D, N), D, delta_bias (nd*D,); B, C (B, nd*G, N, L),
+    any strides (e.g. permuted views of x_proj's output); z (B, D, L): ONE gate shared by the blocks (or (B, nd*D, L)).
+    Block k visits the tokens in order dirs[k] in ('fwd', 'rev', 'frames'); every tensor stays in memory order.
+    Gradient of z: summed over the blocks when z is shared."""
+
+    @staticmethod
+    def forward(ctx, u, delta, A, B, C, D, z, delta_bias, delta_softplus, dirs, nframes):
+        u, delta, z = _last_contig(u), _last_contig(delta), _last_contig(z)
+        out, chk, _, *rest = selective_scan_cuda.fwd(u, delta, A, B, C, D, z, delta_bias, delta_softplus,
+                                                     want_out=z is None, dirs=dirs, nframes=nframes)
+        ctx.delta_softplus, ctx.dirs, ctx.nframes = delta_softplus, dirs, nframes
+        ctx.save_for_backward(u, delta, A, B, C, D, z, delta_bias, chk)
+        return rest[0] if z is not None else out
+
+    @staticmethod
+    def backward(ctx, dout):
+        u, delta, A, B, C, D, z, delta_bias, chk = ctx.saved_tensors
+        nd = len(ctx.dirs)
+        shared = z is not None and z.shape[1] != u.shape[1]
+        if shared:
+            # the blocks are gated by the same z: the op's output is (B, nd*D, L), so each block has its own upstream
+            # gradient rows -- run the backward with full-width gate tensors
+            z_full = z.repeat(1, nd, 1)
+        else:
+            z_full = z
+        du, ddelta, dA, dB, dC, dD, ddelta_bias, *rest = selective_scan_cuda.bwd(
+            u, delta, A, B, C, D, z_full, delta_bias, _last_contig(dout), chk, None, ctx.delta_softplus,
+            dirs=ctx.dirs, nframes=ctx.nframes)
+        dz = rest[0] if z is not None else None
+        if shared:
+            dz = dz.view(dz.shape[0], nd, -1, dz.shape[2]).sum(1).to(z.dtype)
+        return du, ddelta, dA, dB, dC, dD, dz, ddelta_bias, None, None, None
+
+
+def selective_scan_dirs_fn(u, delta, A, B, C, D=None, z=None, delta_bias=None, delta_softplus=False,
+                           dirs=("fwd", "rev", "frames"), nframes=5):
+    """Multi-direction selective scan, see SelectiveScanDirsFn.  B / C must be 4-D (batch, groups, dstate, seqlen)."""
+    return SelectiveScanDirsFn.apply(u, delta, A, B, C, D, z, delta_bias, delta_softplus, tuple(dirs), int(nframes))
+
+
 def selective_scan_ref(u, delta, A, B, C, D=None, z=None, delta_bias=None, delta_softplus=False,
                        return_last_state=False):
     """Pure-torch statement of the op's semantics for real A (reference:

@@ -13,10 +13,12 @@ bit-identical parameters -- checked on CPU against the reference constructor by 
     decoder.*                                SegFormer decode head (its classifier is present but unused)
     out                                      1x1 conv to the classes
 
-Not reproduced: ``from_pretrained`` (no network here: the SegFormer-b3 backbone is built from its config), the
-``with_edge`` head, and the host-RNG coin flip that applies extra feature dropout in training mode
-(modeling/vivim.py:311) -- a deterministic dropout of the same rate is applied to every feature map instead, which
-also keeps the training step capturable in a CUDA graph.
+Not reproduced: ``from_pretrained`` (no network here: the SegFormer-b3 backbone is built from its config) and the
+``with_edge`` head.  The coin flip that applies extra feature dropout to each decoder input in training mode
+(modeling/vivim.py:310-312: ``if torch.rand(1).item() > 0.5``, a host synchronisation) is drawn ON THE DEVICE here --
+same probability, same dropout rate -- so that the training step stays capturable in a CUDA graph.
+
+``RecallFocusedLoss`` restates the training recipe's loss (multiclass_training_folds.py:217-256, 339-361, 363-425).
 """
 from __future__ import annotations
 
@@ -156,7 +158,11 @@ class VivimSegmenter(nn.Module):
             n, _, height, width = fmap.shape
             up = proj(fmap).transpose(1, 2).reshape(n, -1, height, width)
             up = F.interpolate(up, size=size, mode="bilinear", align_corners=False)
-            maps.append(F.dropout(up, p=self.dropout_rate / 4, training=self.training))
+            if self.training:
+                # vivim.py:310-312: with probability 1/2 drop features at rate dropout_rate/2 -- coin drawn on the device
+                coin = torch.rand((), device=up.device) > 0.5
+                up = torch.where(coin, F.dropout(up, p=self.dropout_rate / 2, training=True), up)
+            maps.append(up)
         fused = head.activation(head.batch_norm(head.linear_fuse(torch.cat(maps[::-1], dim=1))))
         fused = head.dropout(head.dropout(fused))
         return self.out(self.feature_dropout(fused))
@@ -168,3 +174,32 @@ class VivimSegmenter(nn.Module):
 
 
 Vivim = VivimSegmenter
+
+
+class RecallFocusedLoss(nn.Module):
+    """``recall_focused_loss`` of the training recipe (multiclass_training_folds.py:339-361):
+    0.4 * class-balanced focal loss (alpha = [0.05, 0.475, 0.475], gamma = 2; :363-425) + 0.6 * Tversky loss
+    (alpha 0.3, beta 0.7; :217-256).  logits (N, C, H, W), targets (N, H, W) integer labels.  The class weights live in
+    a buffer (the reference builds them with torch.tensor(...).to(device) on every call, a host-to-device copy that a
+    CUDA-graph capture cannot contain)."""
+
+    def __init__(self, class_weights=(0.05, 0.475, 0.475), gamma=2.0, tversky_alpha=0.3, tversky_beta=0.7, smooth=1e-6):
+        super().__init__()
+        self.register_buffer("class_weights", torch.tensor(class_weights, dtype=torch.float32))
+        self.gamma, self.ta, self.tb, self.smooth = gamma, tversky_alpha, tversky_beta, smooth
+
+    def forward(self, logits, targets):
+        C = logits.shape[1]
+        probs = F.softmax(logits.float(), dim=1)
+        onehot = F.one_hot(targets.long(), num_classes=C).permute(0, 3, 1, 2).float()
+        # Tversky, per class and per image, then averaged (:240-256)
+        tp = (probs * onehot).sum(dim=(2, 3))
+        fp = (probs * (1 - onehot)).sum(dim=(2, 3))
+        fn = ((1 - probs) * onehot).sum(dim=(2, 3))
+        tversky = (1 - ((tp + self.smooth) / (tp + self.ta * fp + self.tb * fn + self.smooth)).mean(dim=0)).sum() / C
+        # class-balanced focal loss (:405-425)
+        weight = onehot * (1 - probs) ** self.gamma + (1 - onehot) * probs ** self.gamma
+        bce = -onehot * torch.log(probs + 1e-6) - (1 - onehot) * torch.log(1 - probs + 1e-6)
+        focal = (self.class_weights.view(1, C, 1, 1) * weight * bce).mean(dim=(0, 2, 3)).sum()
+        return 0.4 * focal + 0.6 * tversky
+
