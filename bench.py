@@ -771,9 +771,15 @@ def main():
     ap.add_argument("--impl", choices=("ours", "reference"), default="ours")
     ap.add_argument("--clips", type=int, default=1, help="clips per GPU (BASELINE configs[1]: 1)")
     ap.add_argument("--dirs", type=int, default=3, choices=(1, 2, 3), help="direction scans per block (Vivim's v3: 3)")
+    ap.add_argument("--dir-modes", default=None, help="kernel development: comma list overriding the traversal order of the "
+                                                      "direction blocks, e.g. fwd,fwd,fwd")
     ap.add_argument("--no-vivim", action="store_true", help="skip the whole-network clips/s legs")
     ap.add_argument("--quick", action="store_true", help="kernel development: skip the slow side measurements")
     args = ap.parse_args()
+    if args.dir_modes:
+        global DIRS
+        DIRS = tuple(args.dir_modes.split(","))
+        args.dirs = len(DIRS)
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))

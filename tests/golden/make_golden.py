@@ -9,6 +9,7 @@ committed.  What is imported, unmodified, from the reference:
 * ``causal_conv1d_ref``  causal-conv1d/causal_conv1d/causal_conv1d_interface.py:49-65
 * ``selective_scan_ref`` mamba/mamba_ssm/ops/selective_scan_interface.py:86-152
 * ``mamba_inner_ref``    mamba/mamba_ssm/ops/selective_scan_interface.py:636-670
+* ``bimamba_inner_ref``  mamba/mamba_ssm/ops/selective_scan_interface.py:673-709
 * ``Mamba`` (v3 forward) mamba/mamba_ssm/modules/mamba_simple.py:188-264
 
 The two compiled modules (``causal_conv1d_cuda``, ``selective_scan_cuda``) are stubbed; inside the
@@ -197,8 +198,39 @@ def gen_inner_and_module(ssi, ms):
     save("mamba_v3_module", hidden=npy(h), dout=npy(g), out=npy(y), dhidden=npy(h.grad), **arrays)
 
 
+def gen_bimamba(ssi):
+    """bimamba_inner_ref (shared conv / projections, forward scan with A + reversed scan with A_b, out_proj).  The
+    reference's own test compares bimamba_inner_fn with ITSELF (tests/ops/test_selective_scan.py:314-320), so this
+    fixture is the only thing that pins the function."""
+    torch.random.manual_seed(5)
+    nb, nd, ns, rank, L, K, dm = 2, 24, 16, 3, 200, 4, 12
+    xz = torch.randn(nb, 2 * nd, L, requires_grad=True)
+    conv_w = (0.5 * torch.randn(nd, 1, K)).requires_grad_()
+    conv_b = (0.1 * torch.randn(nd)).requires_grad_()
+    x_proj_w = (torch.randn(rank + 2 * ns, nd) / np.sqrt(nd)).requires_grad_()
+    dt_proj_w = (torch.randn(nd, rank) / np.sqrt(rank)).requires_grad_()
+    out_w = (torch.randn(dm, nd) / np.sqrt(nd)).requires_grad_()
+    out_b = (0.1 * torch.randn(dm)).requires_grad_()
+    A = (-torch.arange(1, ns + 1, dtype=torch.float32)).repeat(nd, 1).requires_grad_()
+    A_b = (-0.5 * torch.rand(nd, ns) - 0.1).requires_grad_()
+    D = torch.randn(nd, requires_grad=True)
+    dt_bias = (torch.rand(nd) - 4.0).requires_grad_()
+    y = ssi.bimamba_inner_ref(xz, conv_w, conv_b, x_proj_w, dt_proj_w, out_w, out_b, A, A_b, None, None, D,
+                              delta_bias=dt_bias, delta_softplus=True)
+    g = torch.randn_like(y)
+    y.backward(g)
+    save("bimamba_inner", xz=npy(xz), conv_w=npy(conv_w), conv_b=npy(conv_b), x_proj_w=npy(x_proj_w),
+         dt_proj_w=npy(dt_proj_w), out_w=npy(out_w), out_b=npy(out_b), A=npy(A), A_b=npy(A_b), D=npy(D),
+         dt_bias=npy(dt_bias), dout=npy(g), out=npy(y), dxz=npy(xz.grad), dconv_w=npy(conv_w.grad),
+         dconv_b=npy(conv_b.grad), dx_proj_w=npy(x_proj_w.grad), ddt_proj_w=npy(dt_proj_w.grad),
+         dout_w=npy(out_w.grad), dout_b=npy(out_b.grad), dA=npy(A.grad), dA_b=npy(A_b.grad), dD=npy(D.grad),
+         ddt_bias=npy(dt_bias.grad))
+
+
 if __name__ == "__main__":
     cci, ssi, ms = load_reference()
-    gen_scan(ssi)
-    gen_conv(cci)
-    gen_inner_and_module(ssi, ms)
+    if "--only-bimamba" not in sys.argv:
+        gen_scan(ssi)
+        gen_conv(cci)
+        gen_inner_and_module(ssi, ms)
+    gen_bimamba(ssi)

@@ -147,3 +147,19 @@ def test_mamba_v3_full_stage1_size_matches_reference(cuda_device):
     assert got.shape == g["y_sub"].shape
     err = float(np.abs(got - g["y_sub"]).max()) / float(g["y_absmax"])
     assert err < 2e-3, err
+
+
+def test_bimamba_inner_fn_matches_reference_golden(cuda_device):
+    """bimamba_inner_fn against the reference's bimamba_inner_ref run on CPU (tests/golden/make_golden.py::gen_bimamba):
+    output and every gradient.  The reference's own test compares the function with itself."""
+    from mamba_ssm.ops.selective_scan_interface import bimamba_inner_fn
+    g = golden("bimamba_inner")
+    names = ("xz", "conv_w", "conv_b", "x_proj_w", "dt_proj_w", "out_w", "out_b", "A", "A_b", "D", "dt_bias")
+    t = {k: dev(g[k], torch.float32, grad=True) for k in names}
+    y = bimamba_inner_fn(t["xz"], t["conv_w"], t["conv_b"], t["x_proj_w"], t["dt_proj_w"], t["out_w"], t["out_b"],
+                         t["A"], t["A_b"], None, None, t["D"], delta_bias=t["dt_bias"], delta_softplus=True)
+    y.backward(dev(g["dout"], torch.float32))
+    got = {"out": host(y)}
+    got.update({"d" + k: host(t[k].grad) for k in names})
+    want = {k: g[k] for k in got}
+    compare(got, want, 2e-3, 2e-3, label="bimamba_inner fp32")

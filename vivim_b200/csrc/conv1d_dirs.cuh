@@ -125,6 +125,139 @@ __device__ __forceinline__ DirsGeom dirs_geom(const vv_conv1d_dirs_args& a, int 
     return g;
 }
 
+// ---------------------------------------------------------------- 128-bit path: 4 consecutive pixels per thread
+// (hw % 8 == 0, pt % 8 == 0: a quad never straddles a frame or the end of the sequence).  W holds the own row
+// x[q0-4 .. q0+7]; the taps of FWD / REV are compile-time offsets into it, a FRAMES tap is a window V = row[q0-4 .. q0+3] of
+// another frame shifted by s pixels (warp-uniform), resolved by a 4-way switch so that register indices stay static.
+__device__ __forceinline__ void load_f4(const float* __restrict__ p, float* v) {
+    const float4 x = *reinterpret_cast<const float4*>(p);
+    v[0] = x.x; v[1] = x.y; v[2] = x.z; v[3] = x.w;
+}
+
+template <int S>
+__device__ __forceinline__ void add_shifted(float (&acc)[4], float w, const float (&V)[8]) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) acc[i] = fmaf(w, V[4 + i - S], acc[i]);
+}
+__device__ __forceinline__ void add_shifted_by(int s, float (&acc)[4], float w, const float (&V)[8]) {
+    switch (s) {
+        case 0: add_shifted<0>(acc, w, V); break;
+        case 1: add_shifted<1>(acc, w, V); break;
+        case 2: add_shifted<2>(acc, w, V); break;
+        default: add_shifted<3>(acc, w, V); break;
+    }
+}
+// the same towards the readers (pixels to the right): V = row[q0 .. q0+7], value at index i + S
+template <int S>
+__device__ __forceinline__ void add_ahead(float (&acc)[4], float w, const float (&V)[8]) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) acc[i] = fmaf(w, V[i + S], acc[i]);
+}
+__device__ __forceinline__ void add_ahead_by(int s, float (&acc)[4], float w, const float (&V)[8]) {
+    switch (s) {
+        case 0: add_ahead<0>(acc, w, V); break;
+        case 1: add_ahead<1>(acc, w, V); break;
+        case 2: add_ahead<2>(acc, w, V); break;
+        default: add_ahead<3>(acc, w, V); break;
+    }
+}
+
+// frame / pixel shift of tap kk (kk tokens back) of frame t in FRAMES order
+__device__ __forceinline__ void frames_source(const DirsGeom& g, int t, int kk, int& ts, int& s) {
+    s = kk > t ? (kk - t + g.nf - 1) / g.nf : 0;
+    ts = t - kk + s * g.nf;
+}
+__device__ __forceinline__ void frames_reader(const DirsGeom& g, int t, int kk, int& tr, int& s) {
+    s = (t + kk) / g.nf;
+    tr = t + kk - s * g.nf;
+}
+
+// pre-activations of 4 consecutive pixels q0..q0+3 of frame t, direction `mode`, summed oldest tap first like
+// conv1d_fwd_kernel (bit-identical results).  W = own row [q0-4, q0+8).
+__device__ __forceinline__ void pre_quad(const float* __restrict__ xs, const DirsGeom& g, int mode, int t, int q0,
+                                         const float (&W)[12], const float (&taps)[4], float bias, float (&acc)[4]) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) acc[i] = bias;
+    if (mode == VV_DIR_FWD) {
+#pragma unroll
+        for (int kk = 3; kk >= 0; --kk)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) acc[i] = fmaf(taps[3 - kk], W[4 + i - kk], acc[i]);
+    } else if (mode == VV_DIR_REV) {
+#pragma unroll
+        for (int kk = 3; kk >= 0; --kk)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) acc[i] = fmaf(taps[3 - kk], W[4 + i + kk], acc[i]);
+    } else {
+#pragma unroll
+        for (int kk = 3; kk >= 1; --kk) {
+            int ts, sft;
+            frames_source(g, t, kk, ts, sft);
+            float V[8];
+            const float* r2 = xs + ts * g.pitch + kDirsHalo + q0;
+            load_f4(r2 - 4, V);
+            load_f4(r2, V + 4);
+            if (g.p0 + q0 == 0) V[0] = V[1] = V[2] = V[3] = 0.f;   // pixels before the first one: start of the sequence
+            add_shifted_by(sft, acc, taps[3 - kk], V);
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) acc[i] = fmaf(taps[3], W[4 + i], acc[i]);
+    }
+}
+
+// src[kk][i] = the token kk positions back of pixel q0 + i (frame t) in direction `mode`
+__device__ __forceinline__ void quad_sources(const float* __restrict__ xs, const DirsGeom& g, int mode, int t, int q0,
+                                             const float (&W)[12], float (&src)[4][4]) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) src[0][i] = W[4 + i];
+    if (mode == VV_DIR_FWD) {
+#pragma unroll
+        for (int kk = 1; kk < 4; ++kk)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) src[kk][i] = W[4 + i - kk];
+    } else if (mode == VV_DIR_REV) {
+#pragma unroll
+        for (int kk = 1; kk < 4; ++kk)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) src[kk][i] = W[4 + i + kk];
+    } else {
+#pragma unroll
+        for (int kk = 1; kk < 4; ++kk) {
+            int ts, sft;
+            frames_source(g, t, kk, ts, sft);
+            float V[8];
+            const float* r2 = xs + ts * g.pitch + kDirsHalo + q0;
+            load_f4(r2 - 4, V);
+            load_f4(r2, V + 4);
+            if (g.p0 + q0 == 0) V[0] = V[1] = V[2] = V[3] = 0.f;
+            float tmp[4] = {0.f, 0.f, 0.f, 0.f};
+            add_shifted_by(sft, tmp, 1.f, V);          // tmp[i] = V[4 + i - sft]
+#pragma unroll
+            for (int i = 0; i < 4; ++i) src[kk][i] = tmp[i];
+        }
+    }
+}
+
+template <typename T>
+__device__ __forceinline__ void store4(T* __restrict__ p, const float (&v)[4]);
+template <> __device__ __forceinline__ void store4<float>(float* __restrict__ p, const float (&v)[4]) {
+    *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+}
+template <> __device__ __forceinline__ void store4<__nv_bfloat16>(__nv_bfloat16* __restrict__ p, const float (&v)[4]) {
+    const __nv_bfloat162 a = __floats2bfloat162_rn(v[0], v[1]), b = __floats2bfloat162_rn(v[2], v[3]);
+    uint2 r;
+    r.x = *reinterpret_cast<const uint32_t*>(&a);
+    r.y = *reinterpret_cast<const uint32_t*>(&b);
+    *reinterpret_cast<uint2*>(p) = r;
+}
+template <> __device__ __forceinline__ void store4<__half>(__half* __restrict__ p, const float (&v)[4]) {
+    const __half2 a = __floats2half2_rn(v[0], v[1]), b = __floats2half2_rn(v[2], v[3]);
+    uint2 r;
+    r.x = *reinterpret_cast<const uint32_t*>(&a);
+    r.y = *reinterpret_cast<const uint32_t*>(&b);
+    *reinterpret_cast<uint2*>(p) = r;
+}
+
 // smem: [x tile: nf x pitch floats]
 template <typename T, bool kSilu, bool kVec>
 __global__ void __launch_bounds__(kDirsThreads) conv1d_dirs_fwd_kernel(const vv_conv1d_dirs_args a, const int pt) {
@@ -135,6 +268,38 @@ __global__ void __launch_bounds__(kDirsThreads) conv1d_dirs_fwd_kernel(const vv_
     const int b = row / a.dim, d = row - b * a.dim;
     stage_tile<T, kVec>(xs, reinterpret_cast<const T*>(a.x) + b * a.x_bs + d * a.x_ds, g);
     __syncthreads();
+    if (kVec) {
+        float wd[VV_MAX_DIRS][4], bd[VV_MAX_DIRS];
+#pragma unroll
+        for (int k = 0; k < VV_MAX_DIRS; ++k)
+            if (k < a.ndirs) load_dir_taps(a, k, d, wd[k], bd[k]);
+        const int quads = g.pt / 4;
+        for (int t = 0; t < g.nf; ++t) {
+            for (int qi = threadIdx.x; qi < quads; qi += kDirsThreads) {
+                const int q0 = qi * 4;
+                if (g.p0 + q0 >= g.hw) break;
+                const float* row = xs + t * g.pitch + kDirsHalo + q0;
+                float W[12];
+                load_f4(row - 4, W);
+                load_f4(row, W + 4);
+                load_f4(row + 4, W + 8);
+#pragma unroll
+                for (int k = 0; k < VV_MAX_DIRS; ++k) {
+                    if (k < a.ndirs) {
+                        float acc[4];
+                        pre_quad(xs, g, a.dir_mode[k], t, q0, W, wd[k], bd[k], acc);
+                        if (kSilu) {
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) acc[i] *= sigmoid_f(acc[i]);
+                        }
+                        store4<T>(reinterpret_cast<T*>(a.out) + b * a.out_bs + ((int64_t)k * a.dim + d) * a.out_ds
+                                      + t * g.hw + g.p0 + q0, acc);
+                    }
+                }
+            }
+        }
+        return;
+    }
     for (int k = 0; k < a.ndirs; ++k) {
         const int mode = a.dir_mode[k];
         float taps[4], bias;
@@ -169,15 +334,52 @@ __global__ void __launch_bounds__(kDirsThreads) conv1d_dirs_bwd_kernel(const vv_
     __syncthreads();
     // ---- dout -> d(pre-activation), in place, body and halo; parameter-gradient partial sums over the body
     const int span = g.pt + 2 * (kDirsHalo - 1);
+    const int qv = min(g.pt, g.hw - g.p0);       // pixels of the tile that exist
     for (int k = 0; k < a.ndirs; ++k) {
         const int mode = a.dir_mode[k];
         float taps[4], bias;
         load_dir_taps(a, k, d, taps, bias);
         float* dp = xs + (k + 1) * tile_words;
         float part[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+        if (kVec) {
+            // body: 4 pixels per thread
+            for (int t = 0; t < g.nf; ++t) {
+                for (int qi = threadIdx.x; qi < qv / 4; qi += kDirsThreads) {
+                    const int q0 = qi * 4;
+                    const float* row = xs + t * g.pitch + kDirsHalo + q0;
+                    float W[12], src[4][4], gr[4];
+                    load_f4(row - 4, W);
+                    load_f4(row, W + 4);
+                    load_f4(row + 4, W + 8);
+                    quad_sources(xs, g, mode, t, q0, W, src);
+                    float* dq = dp + t * g.pitch + kDirsHalo + q0;
+                    load_f4(dq, gr);
+                    if (kSilu) {
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            float pre = bias;
+#pragma unroll
+                            for (int kk = 3; kk >= 0; --kk) pre = fmaf(taps[3 - kk], src[kk][i], pre);
+                            const float sg = sigmoid_f(pre);
+                            gr[i] *= sg * (1.f + pre * (1.f - sg));
+                        }
+                    }
+                    *reinterpret_cast<float4*>(dq) = make_float4(gr[0], gr[1], gr[2], gr[3]);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        part[4] += gr[i];
+#pragma unroll
+                        for (int kk = 0; kk < 4; ++kk) part[3 - kk] = fmaf(gr[i], src[kk][i], part[3 - kk]);
+                    }
+                }
+            }
+        }
         for (int t = 0; t < g.nf; ++t) {
-            for (int qq = threadIdx.x; qq < span; qq += kDirsThreads) {
-                const int q = qq - (kDirsHalo - 1);
+            // element-wise route: everything (kVec = false) or just the 3 positions on either side of the body
+            const int nq = kVec ? 2 * (kDirsHalo - 1) : span;
+            for (int qq = threadIdx.x; qq < nq; qq += kDirsThreads) {
+                const int q = kVec ? (qq < kDirsHalo - 1 ? qq - (kDirsHalo - 1) : qv + qq - (kDirsHalo - 1))
+                                   : qq - (kDirsHalo - 1);
                 const int p = g.p0 + q, m = t * g.hw + p;
                 // a token exists in this direction's sequence iff its memory index is in range (FWD / REV: rows are
                 // contiguous, a halo position may belong to the neighbouring frame) / its pixel is (FRAMES)
@@ -220,7 +422,49 @@ __global__ void __launch_bounds__(kDirsThreads) conv1d_dirs_bwd_kernel(const vv_
         if (k < a.ndirs) load_dir_taps(a, k, d, wd[k], bias_unused);
     }
     T* __restrict__ dx = reinterpret_cast<T*>(a.dx) + b * a.dx_bs + d * a.dx_ds;
-    for (int t = 0; t < g.nf; ++t) {
+    if (kVec) {
+        for (int t = 0; t < g.nf; ++t) {
+            for (int qi = threadIdx.x; qi < qv / 4; qi += kDirsThreads) {
+                const int q0 = qi * 4;
+                float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+                for (int k = 0; k < VV_MAX_DIRS; ++k) {
+                    if (k < a.ndirs) {
+                        const int mode = a.dir_mode[k];
+                        const float* dq = xs + (k + 1) * tile_words + t * g.pitch + kDirsHalo + q0;
+                        float Dw[8];
+                        if (mode == VV_DIR_FWD) {              // readers q + kk
+                            load_f4(dq, Dw);
+                            load_f4(dq + 4, Dw + 4);
+#pragma unroll
+                            for (int kk = 0; kk < 4; ++kk)
+#pragma unroll
+                                for (int i = 0; i < 4; ++i) acc[i] = fmaf(wd[k][3 - kk], Dw[i + kk], acc[i]);
+                        } else if (mode == VV_DIR_REV) {       // readers q - kk
+                            load_f4(dq - 4, Dw);
+                            load_f4(dq, Dw + 4);
+#pragma unroll
+                            for (int kk = 0; kk < 4; ++kk)
+#pragma unroll
+                                for (int i = 0; i < 4; ++i) acc[i] = fmaf(wd[k][3 - kk], Dw[4 + i - kk], acc[i]);
+                        } else {                               // readers in frame tr, s pixels to the right
+#pragma unroll
+                            for (int kk = 0; kk < 4; ++kk) {
+                                int tr, sft;
+                                frames_reader(g, t, kk, tr, sft);
+                                const float* dr = xs + (k + 1) * tile_words + tr * g.pitch + kDirsHalo + q0;
+                                load_f4(dr, Dw);
+                                load_f4(dr + 4, Dw + 4);
+                                add_ahead_by(sft, acc, wd[k][3 - kk], Dw);
+                            }
+                        }
+                    }
+                }
+                store4<T>(dx + t * g.hw + g.p0 + q0, acc);
+            }
+        }
+    }
+    for (int t = 0; t < (kVec ? 0 : g.nf); ++t) {
         for (int q = threadIdx.x; q < g.pt; q += kDirsThreads) {
             if (g.p0 + q >= g.hw) break;
             float acc = 0.f;

@@ -173,8 +173,9 @@ int launch_conv_dirs(const vv_conv1d_dirs_args* a, void* stream) {
     if (!elem_aligned(a->x, es) || !elem_aligned(a->out, es) || !elem_aligned(a->dout, es) || !elem_aligned(a->dx, es))
         return fail(VV_ERR_ALIGN, "conv1d_dirs: tensor not aligned to its element size");
     const int nf = b.nframes, hw = b.seqlen / nf;
-    // pixels per CTA: about 1280 tokens of every direction, a multiple of the thread count
-    const int pt = std::max(128, std::min(1024, (1280 / nf) / 128 * 128));
+    // pixels per CTA: one 4-pixel quad per thread and frame (two without frames), shrunk until the tiles fit 64 KB
+    int pt = nf >= 3 ? 512 : 1024;
+    while (pt > 128 && (size_t)(kBwd ? a->ndirs + 1 : 1) * nf * (pt + 2 * vv::kDirsHalo) * sizeof(float) > 64 * 1024) pt -= 128;
     if ((int64_t)a->batch * a->dim > 2147483647ll || (hw + pt - 1) / pt > 65535)
         return fail(VV_ERR_UNSUPPORTED, "conv1d_dirs: grid too large");
     bool vec = hw % 8 == 0 && vec_ok(a->x, es, {a->x_bs, a->x_ds});
