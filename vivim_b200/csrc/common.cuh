@@ -181,6 +181,51 @@ __device__ __forceinline__ void store8_trav(T* __restrict__ row, int j0, const T
     }
 }
 
+// ---------------------------------------------------------------- FRAMES order, coalesced
+// The 64 traversal positions [j0, j0+64) of a FRAMES-ordered row are, in memory, nf short runs of consecutive pixels
+// (one per frame, ~64/nf pixels each).  Reading them position by position costs one 2-byte access per element and lane,
+// every warp-wide request touching up to 32 sectors; here the lanes that share a row walk the runs instead (consecutive
+// lanes = consecutive pixels: one or two sectors per run) and drop the elements into a shared-memory row in TRAVERSAL
+// order, from which every lane takes its 8 positions with one 128-bit read.  FramesSpan holds the run boundaries of one
+// segment (two integer divisions per CTA instead of two per element).
+struct FramesSpan {
+    int p_first, t_first;   // pixel / frame of position j0
+    int p_last, t_last;     // pixel / frame of the last position of the span that exists (< L)
+    int j0;
+};
+__device__ __forceinline__ FramesSpan frames_span(const Trav& tr, int j0, int len) {
+    FramesSpan s;
+    s.j0 = j0;
+    s.p_first = j0 / tr.nf;
+    s.t_first = j0 - s.p_first * tr.nf;
+    const int je = min(j0 + len, tr.L) - 1;
+    s.p_last = je / tr.nf;
+    s.t_last = je - s.p_last * tr.nf;
+    return s;
+}
+// `sub` of `nl` lanes: global row (memory order) -> shared row dst[0..len) (traversal order)
+template <typename T>
+__device__ __forceinline__ void frames_gather(T* __restrict__ dst, const T* __restrict__ row, const FramesSpan& s,
+                                              const Trav& tr, int sub, int nl) {
+    if (s.j0 >= tr.L) return;
+    for (int t = 0; t < tr.nf; ++t) {
+        const int plo = s.p_first + (t < s.t_first ? 1 : 0), phi = s.p_last - (t > s.t_last ? 1 : 0);
+        const T* src = row + (int64_t)t * tr.hw;
+        for (int p = plo + sub; p <= phi; p += nl) dst[p * tr.nf + t - s.j0] = src[p];
+    }
+}
+// shared row src[0..len) (traversal order) -> global row (memory order)
+template <typename T>
+__device__ __forceinline__ void frames_scatter(T* __restrict__ row, const T* __restrict__ src, const FramesSpan& s,
+                                               const Trav& tr, int sub, int nl) {
+    if (s.j0 >= tr.L) return;
+    for (int t = 0; t < tr.nf; ++t) {
+        const int plo = s.p_first + (t < s.t_first ? 1 : 0), phi = s.p_last - (t > s.t_last ? 1 : 0);
+        T* dst = row + (int64_t)t * tr.hw;
+        for (int p = plo + sub; p <= phi; p += nl) dst[p] = src[p * tr.nf + t - s.j0];
+    }
+}
+
 // ---------------------------------------------------------------- deferred unpacking
 // Raw8 holds the 8 positions of a row segment as loaded (16 or 32 bytes of registers), so that a
 // kernel can issue ALL of its global loads first and convert later: the DRAM latency of a
@@ -193,6 +238,14 @@ template <typename T> struct Raw8<T, true> {
         if (t0 >= 0 && t0 < L) {
             lo = __ldg(reinterpret_cast<const uint4*>(row + t0));
             if (sizeof(T) == 4) hi = __ldg(reinterpret_cast<const uint4*>(row + t0) + 1);
+        }
+    }
+    // 8 positions of a staged (traversal-ordered, 16-byte aligned) shared-memory row; positions >= L read as 0
+    __device__ __forceinline__ void load_staged(const T* srow, int j, int j0, int L) {
+        lo = hi = make_uint4(0, 0, 0, 0);
+        if (j0 >= 0 && j0 < L) {
+            lo = *reinterpret_cast<const uint4*>(srow + j);
+            if (sizeof(T) == 4) hi = *(reinterpret_cast<const uint4*>(srow + j) + 1);
         }
     }
     // positions [j0, j0+8) in traversal order (all inside or all outside [0, L): L % 8 == 0, j0 % 8 == 0)
@@ -263,6 +316,10 @@ template <typename T> struct Raw8<T, false> {
             const int j = j0 + i;
             f[i] = (j >= 0 && j < tr.L) ? to_f32<T>(row[tr.mem(j)]) : 0.f;
         }
+    }
+    __device__ __forceinline__ void load_staged(const T* srow, int j, int j0, int L) {   // element-wise twin (unused route)
+#pragma unroll
+        for (int i = 0; i < 8; ++i) f[i] = (j0 >= 0 && j0 + i < L) ? to_f32<T>(srow[j + i]) : 0.f;
     }
     __device__ __forceinline__ void unpack(float (&v)[8]) const {
 #pragma unroll

@@ -164,10 +164,29 @@ __global__ void __launch_bounds__(kBwdThreads, 4) seg_bwd_kernel(const vv_scan_a
 
     // ---- every global load that does not depend on the preceding kernels, issued up front
     Raw8<T, kVec> r_dt, r_u, r_g, r_z;
-    r_dt.load_trav(reinterpret_cast<const T*>(a.delta) + b * a.delta_bs + d * a.delta_ds, t0, tr);
-    r_u.load_trav(reinterpret_cast<const T*>(a.u) + b * a.u_bs + d * a.u_ds, t0, tr);
-    r_g.load_trav(reinterpret_cast<const T*>(a.dout) + b * a.dout_bs + dg * a.dout_ds, t0, tr);
-    if (a.z) r_z.load_trav(reinterpret_cast<const T*>(a.z) + b * a.z_bs + dg * a.z_ds, t0, tr);
+    const bool staged = kVec && tr.mode == VV_DIR_FRAMES;     // FRAMES order: rows gathered run by run through shared memory
+    const FramesSpan span = frames_span(tr, t0s, kSeg);
+    if (staged) {
+        // staging rows of the warp's 4 channels x 4 tensors: the warp's own dB / dC tile, not used before the state loop
+        T* stg = reinterpret_cast<T*>(tdB) + cg * kSeg;
+        if (live) {
+            frames_gather(stg, reinterpret_cast<const T*>(a.delta) + b * a.delta_bs + d * a.delta_ds, span, tr, tb, 8);
+            frames_gather(stg + 4 * kSeg, reinterpret_cast<const T*>(a.u) + b * a.u_bs + d * a.u_ds, span, tr, tb, 8);
+            frames_gather(stg + 8 * kSeg, reinterpret_cast<const T*>(a.dout) + b * a.dout_bs + dg * a.dout_ds, span, tr, tb, 8);
+            if (a.z) frames_gather(stg + 12 * kSeg, reinterpret_cast<const T*>(a.z) + b * a.z_bs + dg * a.z_ds, span, tr, tb, 8);
+        }
+        __syncwarp();
+        r_dt.load_staged(stg, tb * 8, t0, L);
+        r_u.load_staged(stg + 4 * kSeg, tb * 8, t0, L);
+        r_g.load_staged(stg + 8 * kSeg, tb * 8, t0, L);
+        if (a.z) r_z.load_staged(stg + 12 * kSeg, tb * 8, t0, L);
+        __syncwarp();
+    } else {
+        r_dt.load_trav(reinterpret_cast<const T*>(a.delta) + b * a.delta_bs + d * a.delta_ds, t0, tr);
+        r_u.load_trav(reinterpret_cast<const T*>(a.u) + b * a.u_bs + d * a.u_ds, t0, tr);
+        r_g.load_trav(reinterpret_cast<const T*>(a.dout) + b * a.dout_bs + dg * a.dout_ds, t0, tr);
+        if (a.z) r_z.load_trav(reinterpret_cast<const T*>(a.z) + b * a.z_bs + dg * a.z_ds, t0, tr);
+    }
     BwdTileLoader<T, kVec, NB> lB, lC;
     lB.load(reinterpret_cast<const T*>(a.Bm) + b * a.B_bs + grp * a.B_gs, a.B_ns, a.B_ls, N, t0s, tr);
     lC.load(reinterpret_cast<const T*>(a.Cm) + b * a.C_bs + grp * a.C_gs, a.C_ns, a.C_ls, N, t0s, tr);
@@ -396,14 +415,28 @@ __global__ void __launch_bounds__(kBwdThreads, 4) seg_bwd_kernel(const vv_scan_a
             dbias_loc += (t0 + i < L) ? dd : 0.f;
             dD_loc = fmaf(gi, u[i], dD_loc);
         }
-        if (live) {
+        if (a.z) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) dzf[i] *= fmaf(Dv, u[i], (i & 1) ? y2[i >> 1].y : y2[i >> 1].x);
+        }
+        if (staged && 4 * (int)sizeof(T) <= NB) {
+            // FRAMES order: one tensor at a time through a 4-row staging area (the warp's state tables, done with)
+            T* ostg = reinterpret_cast<T*>(tabER) + cg * kSeg;
+#pragma unroll
+            for (int which = 0; which < 3; ++which) {
+                if (which == 2 && !a.z) break;
+                __syncwarp();
+                if (kVec) store8_vec<T>(ostg + tb * 8, which == 0 ? du_o : (which == 1 ? ddt_o : dzf));
+                __syncwarp();
+                T* grow = which == 0 ? reinterpret_cast<T*>(a.du) + b * a.du_bs + d * a.du_ds
+                        : which == 1 ? reinterpret_cast<T*>(a.ddelta) + b * a.ddelta_bs + d * a.ddelta_ds
+                                     : reinterpret_cast<T*>(a.dz) + b * a.dz_bs + d * a.dz_ds;
+                if (live) frames_scatter(grow, ostg, span, tr, tb, 8);
+            }
+        } else if (live) {
             store8_trav<T, kVec>(reinterpret_cast<T*>(a.du) + b * a.du_bs + d * a.du_ds, t0, tr, du_o);
             store8_trav<T, kVec>(reinterpret_cast<T*>(a.ddelta) + b * a.ddelta_bs + d * a.ddelta_ds, t0, tr, ddt_o);
-            if (a.z) {
-#pragma unroll
-                for (int i = 0; i < 8; ++i) dzf[i] *= fmaf(Dv, u[i], (i & 1) ? y2[i >> 1].y : y2[i >> 1].x);
-                store8_trav<T, kVec>(reinterpret_cast<T*>(a.dz) + b * a.dz_bs + d * a.dz_ds, t0, tr, dzf);
-            }
+            if (a.z) store8_trav<T, kVec>(reinterpret_cast<T*>(a.dz) + b * a.dz_bs + d * a.dz_ds, t0, tr, dzf);
         }
 #pragma unroll
         for (int o = 4; o > 0; o >>= 1) {
@@ -489,26 +522,37 @@ constexpr int kCastThreads = 256;
 template <typename T>
 __global__ void __launch_bounds__(kCastThreads) cast_bc_strided_kernel(const vv_scan_args a) {
     __shared__ float tile[2][kMaxState][kSeg + 1];
+    __shared__ int s_mem[kSeg];                       // memory position of each traversal position of the segment
     pdl_wait();
     const int N = a.dstate, L = a.seqlen;
     const int seg = blockIdx.x, g = blockIdx.y, b = blockIdx.z;
     const int t0 = seg * kSeg;
+    const int tid = threadIdx.x;
     const Trav tr = group_trav(a, g);
     const int64_t acc_base = (((int64_t)b * a.ngroups + g) * N) * L;
-    for (int idx = threadIdx.x; idx < 2 * N * kSeg; idx += kCastThreads) {
-        const int which = idx / (N * kSeg), rem = idx - which * N * kSeg;
-        const int n = rem / kSeg, j = rem - n * kSeg;
-        const float* src = which ? a.dC : a.dB;
-        tile[which][n][j] = (t0 + j < L) ? src[acc_base + (int64_t)n * L + t0 + j] : 0.f;
+    if (tid < kSeg) s_mem[tid] = t0 + tid < L ? tr.mem(t0 + tid) : -1;
+    {   // rows of the accumulators: thread = (row n0 + 4 i, position j), 64 consecutive floats per row
+        const int j = tid & (kSeg - 1), n0 = tid >> 6;
+        const bool ok = t0 + j < L;
+        for (int n = n0; n < N; n += kCastThreads / kSeg) {
+            const int64_t o = acc_base + (int64_t)n * L + t0 + j;
+            tile[0][n][j] = ok ? a.dB[o] : 0.f;
+            tile[1][n][j] = ok ? a.dC[o] : 0.f;
+        }
     }
     __syncthreads();
-    for (int idx = threadIdx.x; idx < 2 * N * kSeg; idx += kCastThreads) {
-        const int j = idx / (2 * N), rem = idx - j * 2 * N;
-        const int which = rem / N, n = rem - which * N;
-        if (t0 + j < L) {
-            const int64_t m = tr.mem(t0 + j);
-            if (which) reinterpret_cast<T*>(a.dC_io)[b * a.dCio_bs + g * a.dCio_gs + n * a.dCio_ns + m * a.dCio_ls] = from_f32<T>(tile[1][n][j]);
-            else reinterpret_cast<T*>(a.dB_io)[b * a.dBio_bs + g * a.dBio_gs + n * a.dBio_ns + m * a.dBio_ls] = from_f32<T>(tile[0][n][j]);
+    {   // a warp writes one position at a time: lane = (tensor, state), the state index fastest
+        const int lane = tid & 31, w = tid >> 5;
+        for (int e = lane; e < 2 * N; e += 32) {
+            const int which = e >= N ? 1 : 0, n = e - which * N;
+            T* dst = which ? reinterpret_cast<T*>(a.dC_io) + b * a.dCio_bs + g * a.dCio_gs + n * a.dCio_ns
+                           : reinterpret_cast<T*>(a.dB_io) + b * a.dBio_bs + g * a.dBio_gs + n * a.dBio_ns;
+            const int64_t ls = which ? a.dCio_ls : a.dBio_ls;
+#pragma unroll 4
+            for (int j = w; j < kSeg; j += kCastThreads / 32) {
+                const int m = s_mem[j];
+                if (m >= 0) dst[m * ls] = from_f32<T>(tile[which][n][j]);
+            }
         }
     }
 }

@@ -215,8 +215,33 @@ template <typename T, bool kVec, int kKind>
 struct SegPrepass {
     Raw8<T, kVec> r_dt[2], r_cf[2], r_z[2];
     int t[2];
+    // s_dt / s_cf / s_z: 16-byte aligned shared rows of kSeg elements of T (or NULL) that the FRAMES order may use to
+    // stage this channel's rows (coalesced gather by the 4 lanes of the channel, see frames_gather); they may alias the
+    // tiles that finish() writes later.  Must be called by whole warps.
     __device__ __forceinline__ void load(const T* __restrict__ g_dt, const T* __restrict__ g_cf, const T* __restrict__ g_z,
-                                         bool live, int q, int t0, const Trav& tr) {
+                                         bool live, int q, int t0, const Trav& tr, T* s_dt = nullptr, T* s_cf = nullptr,
+                                         T* s_z = nullptr) {
+        if (kVec && tr.mode == VV_DIR_FRAMES && s_dt != nullptr && s_cf != nullptr) {
+            const FramesSpan sp = frames_span(tr, t0, kSeg);
+            if (live) {
+                frames_gather(s_dt, g_dt, sp, tr, q, 4);
+                frames_gather(s_cf, g_cf, sp, tr, q, 4);
+                if (g_z && s_z) frames_gather(s_z, g_z, sp, tr, q, 4);
+            }
+            __syncwarp();
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+                t[k] = live ? t0 + (q + 4 * k) * 8 : tr.L;
+                r_dt[k].load_staged(s_dt, (q + 4 * k) * 8, t[k], tr.L);
+                r_cf[k].load_staged(s_cf, (q + 4 * k) * 8, t[k], tr.L);
+                if (g_z) {
+                    if (s_z) r_z[k].load_staged(s_z, (q + 4 * k) * 8, t[k], tr.L);
+                    else r_z[k].load_trav(g_z, t[k], tr);
+                }
+            }
+            __syncwarp();   // every lane has its rows in registers before the staging space is reused
+            return;
+        }
 #pragma unroll
         for (int k = 0; k < 2; ++k) {
             t[k] = live ? t0 + (q + 4 * k) * 8 : tr.L;   // dead rows read as padding
@@ -292,12 +317,17 @@ __global__ void __launch_bounds__(kSegThreads, (kVec && NB <= 16 && sizeof(T) ==
     // every global load of the CTA is issued before the first use, so the latencies overlap
     SegPrepass<T, kVec, kRev ? 1 : 0> pre;
     StateTileLoader<T, kVec, NB> st;
+    // FRAMES staging rows: the head of this channel's fp32 tile rows (a 16-bit row needs 128 of the 256 bytes, so z
+    // shares the dt row); fp32 I/O stages dt and the coefficient only
+    T* s_dt = reinterpret_cast<T*>(f_dt + r * kF32Pitch);
+    T* s_cf = reinterpret_cast<T*>(f_cf + r * kF32Pitch);
+    T* s_z = sizeof(T) == 2 ? s_dt + kSeg : nullptr;
     if (!kRev) {
-        pre.load(g_dt, reinterpret_cast<const T*>(a.u) + c.b * a.u_bs + d * a.u_ds, nullptr, live, q, c.t0, c.tr);
+        pre.load(g_dt, reinterpret_cast<const T*>(a.u) + c.b * a.u_bs + d * a.u_ds, nullptr, live, q, c.t0, c.tr, s_dt, s_cf, s_z);
         st.load(reinterpret_cast<const T*>(a.Bm) + c.b * a.B_bs + c.g * a.B_gs, a.B_ns, a.B_ls, N, c.t0, c.tr);
     } else {
         pre.load(g_dt, reinterpret_cast<const T*>(a.dout) + c.b * a.dout_bs + dg * a.dout_ds,
-                 a.z ? reinterpret_cast<const T*>(a.z) + c.b * a.z_bs + dg * a.z_ds : nullptr, live, q, c.t0, c.tr);
+                 a.z ? reinterpret_cast<const T*>(a.z) + c.b * a.z_bs + dg * a.z_ds : nullptr, live, q, c.t0, c.tr, s_dt, s_cf, s_z);
         st.load(reinterpret_cast<const T*>(a.Cm) + c.b * a.C_bs + c.g * a.C_gs, a.C_ns, a.C_ls, N, c.t0, c.tr);
     }
     float A2[NQ], h[NQ];
@@ -474,7 +504,9 @@ __global__ void __launch_bounds__(kSegThreads) seg_fwd_kernel(const vv_scan_args
     StateTileLoader<T, kVec, NB> stB, stC;
     pre.load(reinterpret_cast<const T*>(a.delta) + c.b * a.delta_bs + d * a.delta_ds,
              reinterpret_cast<const T*>(a.u) + c.b * a.u_bs + d * a.u_ds,
-             a.z ? reinterpret_cast<const T*>(a.z) + c.b * a.z_bs + gate_row(a, d) * a.z_ds : nullptr, live, q, c.t0, c.tr);
+             a.z ? reinterpret_cast<const T*>(a.z) + c.b * a.z_bs + gate_row(a, d) * a.z_ds : nullptr, live, q, c.t0, c.tr,
+             reinterpret_cast<T*>(f_dt + r * kF32Pitch), reinterpret_cast<T*>(t_u + r * SegTile<T>::kPitch),
+             reinterpret_cast<T*>(t_z + r * SegTile<T>::kPitch));
     stB.load(reinterpret_cast<const T*>(a.Bm) + c.b * a.B_bs + c.g * a.B_gs, a.B_ns, a.B_ls, N, c.t0, c.tr);
     stC.load(reinterpret_cast<const T*>(a.Cm) + c.b * a.C_bs + c.g * a.C_gs, a.C_ns, a.C_ls, N, c.t0, c.tr);
     float A2[NQ], h[NQ];
@@ -561,7 +593,14 @@ __global__ void __launch_bounds__(kSegThreads) seg_fwd_kernel(const vv_scan_args
         }
     }
     __syncwarp();   // the four lanes of a channel (same warp) wrote its row; each lane now flushes two chunks of it
-    if (live) {
+    if (live && kVec && c.tr.mode == VV_DIR_FRAMES) {
+        // the rows hold the outputs in traversal order: the 4 lanes of the channel write them out run by run
+        const FramesSpan sp = frames_span(c.tr, c.t0, kSeg);
+        if (a.out) frames_scatter(reinterpret_cast<T*>(a.out) + c.b * a.out_bs + d * a.out_ds,
+                                  reinterpret_cast<const T*>(t_z + r * SegTile<T>::kPitch), sp, c.tr, q, 4);
+        if (a.z) frames_scatter(reinterpret_cast<T*>(a.out_z) + c.b * a.outz_bs + d * a.outz_ds,
+                                reinterpret_cast<const T*>(t_u + r * SegTile<T>::kPitch), sp, c.tr, q, 4);
+    } else if (live) {
         const unsigned char* my_u = t_u + r * SegTile<T>::kPitch;
         const unsigned char* my_z = t_z + r * SegTile<T>::kPitch;
 #pragma unroll

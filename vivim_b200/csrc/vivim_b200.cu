@@ -174,7 +174,9 @@ int launch_conv_dirs(const vv_conv1d_dirs_args* a, void* stream) {
         return fail(VV_ERR_ALIGN, "conv1d_dirs: tensor not aligned to its element size");
     const int nf = b.nframes, hw = b.seqlen / nf;
     // pixels per CTA: one 4-pixel quad per thread and frame (two without frames), shrunk until the tiles fit 64 KB
-    int pt = nf >= 3 ? 512 : 1024;
+    static const int pt_env = env_int("VV_DIRS_PT", 0);     // development knob: pixels per CTA
+    int pt = pt_env > 0 ? pt_env / 128 * 128 : (nf >= 3 ? 512 : 1024);
+    if (pt < 128) pt = 128;
     while (pt > 128 && (size_t)(kBwd ? a->ndirs + 1 : 1) * nf * (pt + 2 * vv::kDirsHalo) * sizeof(float) > 64 * 1024) pt -= 128;
     if ((int64_t)a->batch * a->dim > 2147483647ll || (hw + pt - 1) / pt > 65535)
         return fail(VV_ERR_UNSUPPORTED, "conv1d_dirs: grid too large");
