@@ -203,26 +203,82 @@ __device__ __forceinline__ FramesSpan frames_span(const Trav& tr, int j0, int le
     s.t_last = je - s.p_last * tr.nf;
     return s;
 }
-// `sub` of `nl` lanes: global row (memory order) -> shared row dst[0..len) (traversal order)
-template <typename T>
-__device__ __forceinline__ void frames_gather(T* __restrict__ dst, const T* __restrict__ row, const FramesSpan& s,
-                                              const Trav& tr, int sub, int nl) {
-    if (s.j0 >= tr.L) return;
-    for (int t = 0; t < tr.nf; ++t) {
-        const int plo = s.p_first + (t < s.t_first ? 1 : 0), phi = s.p_last - (t > s.t_last ? 1 : 0);
-        const T* src = row + (int64_t)t * tr.hw;
-        for (int p = plo + sub; p <= phi; p += nl) dst[p * tr.nf + t - s.j0] = src[p];
+// `sub` of NL lanes: global row (memory order) -> shared row dst[0..len) (traversal order).  All loads are issued before
+// the first store (a short-lived CTA must not serialise its global latencies): kFramesMaxNf frames x KP pixels per lane,
+// statically unrolled, so the route serves nframes <= kFramesMaxNf with at most NL * KP pixels of a frame per segment
+// (frames_staging_ok); anything else takes the element-wise route.
+constexpr int kFramesMaxNf = 8;
+template <int NL, int KP>
+__host__ __device__ constexpr bool frames_fits(int nf, int len) { return nf >= 2 && nf <= kFramesMaxNf && (len / nf + 2) <= NL * KP; }
+
+template <typename T, int NL, int KP, int NF>
+struct FramesGather {
+    T v[NF][KP];
+    __device__ __forceinline__ void load(const T* __restrict__ row, const FramesSpan& s, const Trav& tr, int sub) {
+#pragma unroll
+        for (int t = 0; t < NF; ++t) {
+            const int plo = s.p_first + (t < s.t_first ? 1 : 0), phi = s.p_last - (t > s.t_last ? 1 : 0);
+#pragma unroll
+            for (int k = 0; k < KP; ++k) {
+                const int p = plo + sub + k * NL;
+                if (t < tr.nf && p <= phi && s.j0 < tr.L) v[t][k] = row[(int64_t)t * tr.hw + p];
+            }
+        }
     }
+    __device__ __forceinline__ void store(T* __restrict__ dst, const FramesSpan& s, const Trav& tr, int sub) const {
+#pragma unroll
+        for (int t = 0; t < NF; ++t) {
+            const int plo = s.p_first + (t < s.t_first ? 1 : 0), phi = s.p_last - (t > s.t_last ? 1 : 0);
+#pragma unroll
+            for (int k = 0; k < KP; ++k) {
+                const int p = plo + sub + k * NL;
+                if (t < tr.nf && p <= phi && s.j0 < tr.L) dst[p * tr.nf + t - s.j0] = v[t][k];
+            }
+        }
+    }
+};
+// NF: static bound on nframes (5 covers Vivim's clips with 3/8 fewer registers in flight than kFramesMaxNf)
+template <typename T, int NL, int KP, int NF>
+__device__ __forceinline__ void frames_gather_n(T* __restrict__ dst, const T* __restrict__ row, const FramesSpan& s,
+                                                const Trav& tr, int sub) {
+    FramesGather<T, NL, KP, NF> g;
+    g.load(row, s, tr, sub);
+    g.store(dst, s, tr, sub);
+}
+template <typename T, int NL, int KP>
+__device__ __forceinline__ void frames_gather(T* __restrict__ dst, const T* __restrict__ row, const FramesSpan& s,
+                                              const Trav& tr, int sub) {
+    if (tr.nf <= 5) frames_gather_n<T, NL, KP, 5>(dst, row, s, tr, sub);
+    else frames_gather_n<T, NL, KP, kFramesMaxNf>(dst, row, s, tr, sub);
+}
+// two rows at once: both rows' loads in flight together
+template <typename T, int NL, int KP, int NF>
+__device__ __forceinline__ void frames_gather2_n(T* __restrict__ dst0, const T* __restrict__ row0, T* __restrict__ dst1,
+                                                 const T* __restrict__ row1, const FramesSpan& s, const Trav& tr, int sub) {
+    FramesGather<T, NL, KP, NF> g0, g1;
+    g0.load(row0, s, tr, sub);
+    g1.load(row1, s, tr, sub);
+    g0.store(dst0, s, tr, sub);
+    g1.store(dst1, s, tr, sub);
+}
+template <typename T, int NL, int KP>
+__device__ __forceinline__ void frames_gather2(T* __restrict__ dst0, const T* __restrict__ row0, T* __restrict__ dst1,
+                                               const T* __restrict__ row1, const FramesSpan& s, const Trav& tr, int sub) {
+    if (tr.nf <= 5) frames_gather2_n<T, NL, KP, 5>(dst0, row0, dst1, row1, s, tr, sub);
+    else frames_gather2_n<T, NL, KP, kFramesMaxNf>(dst0, row0, dst1, row1, s, tr, sub);
 }
 // shared row src[0..len) (traversal order) -> global row (memory order)
-template <typename T>
+template <typename T, int NL, int KP>
 __device__ __forceinline__ void frames_scatter(T* __restrict__ row, const T* __restrict__ src, const FramesSpan& s,
-                                               const Trav& tr, int sub, int nl) {
-    if (s.j0 >= tr.L) return;
-    for (int t = 0; t < tr.nf; ++t) {
+                                               const Trav& tr, int sub) {
+#pragma unroll
+    for (int t = 0; t < kFramesMaxNf; ++t) {
         const int plo = s.p_first + (t < s.t_first ? 1 : 0), phi = s.p_last - (t > s.t_last ? 1 : 0);
-        T* dst = row + (int64_t)t * tr.hw;
-        for (int p = plo + sub; p <= phi; p += nl) dst[p] = src[p * tr.nf + t - s.j0];
+#pragma unroll
+        for (int k = 0; k < KP; ++k) {
+            const int p = plo + sub + k * NL;
+            if (t < tr.nf && p <= phi && s.j0 < tr.L) row[(int64_t)t * tr.hw + p] = src[p * tr.nf + t - s.j0];
+        }
     }
 }
 

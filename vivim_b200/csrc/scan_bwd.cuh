@@ -164,16 +164,18 @@ __global__ void __launch_bounds__(kBwdThreads, 4) seg_bwd_kernel(const vv_scan_a
 
     // ---- every global load that does not depend on the preceding kernels, issued up front
     Raw8<T, kVec> r_dt, r_u, r_g, r_z;
-    const bool staged = kVec && tr.mode == VV_DIR_FRAMES;     // FRAMES order: rows gathered run by run through shared memory
+    constexpr int kKP = 3;                                    // FRAMES staging: 8 lanes x 3 pixels of a frame (nframes >= 3)
+    const bool staged = kVec && tr.mode == VV_DIR_FRAMES && frames_fits<8, kKP>(tr.nf, kSeg);   // rows gathered run by run through shared memory
     const FramesSpan span = frames_span(tr, t0s, kSeg);
     if (staged) {
         // staging rows of the warp's 4 channels x 4 tensors: the warp's own dB / dC tile, not used before the state loop
         T* stg = reinterpret_cast<T*>(tdB) + cg * kSeg;
         if (live) {
-            frames_gather(stg, reinterpret_cast<const T*>(a.delta) + b * a.delta_bs + d * a.delta_ds, span, tr, tb, 8);
-            frames_gather(stg + 4 * kSeg, reinterpret_cast<const T*>(a.u) + b * a.u_bs + d * a.u_ds, span, tr, tb, 8);
-            frames_gather(stg + 8 * kSeg, reinterpret_cast<const T*>(a.dout) + b * a.dout_bs + dg * a.dout_ds, span, tr, tb, 8);
-            if (a.z) frames_gather(stg + 12 * kSeg, reinterpret_cast<const T*>(a.z) + b * a.z_bs + dg * a.z_ds, span, tr, tb, 8);
+            frames_gather2<T, 8, kKP>(stg, reinterpret_cast<const T*>(a.delta) + b * a.delta_bs + d * a.delta_ds,
+                                      stg + 4 * kSeg, reinterpret_cast<const T*>(a.u) + b * a.u_bs + d * a.u_ds, span, tr, tb);
+            if (a.z) frames_gather2<T, 8, kKP>(stg + 8 * kSeg, reinterpret_cast<const T*>(a.dout) + b * a.dout_bs + dg * a.dout_ds,
+                                               stg + 12 * kSeg, reinterpret_cast<const T*>(a.z) + b * a.z_bs + dg * a.z_ds, span, tr, tb);
+            else frames_gather<T, 8, kKP>(stg + 8 * kSeg, reinterpret_cast<const T*>(a.dout) + b * a.dout_bs + dg * a.dout_ds, span, tr, tb);
         }
         __syncwarp();
         r_dt.load_staged(stg, tb * 8, t0, L);
@@ -431,7 +433,7 @@ __global__ void __launch_bounds__(kBwdThreads, 4) seg_bwd_kernel(const vv_scan_a
                 T* grow = which == 0 ? reinterpret_cast<T*>(a.du) + b * a.du_bs + d * a.du_ds
                         : which == 1 ? reinterpret_cast<T*>(a.ddelta) + b * a.ddelta_bs + d * a.ddelta_ds
                                      : reinterpret_cast<T*>(a.dz) + b * a.dz_bs + d * a.dz_ds;
-                if (live) frames_scatter(grow, ostg, span, tr, tb, 8);
+                if (live) frames_scatter<T, 8, kKP>(grow, ostg, span, tr, tb);
             }
         } else if (live) {
             store8_trav<T, kVec>(reinterpret_cast<T*>(a.du) + b * a.du_bs + d * a.du_ds, t0, tr, du_o);

@@ -46,6 +46,7 @@ constexpr int kSeg = 64;                      // positions per segment
 constexpr int kSegRows = 32;                  // channels per CTA
 constexpr int kSegThreads = 4 * kSegRows;     // 4 lanes per channel -> 2 warps
 constexpr int kF32Pitch = kSeg * 4 + 16;      // bytes per row of an fp32 [channel][64] tile (17 x 16)
+constexpr int kSegKP = 4;                     // FRAMES staging: pixels of a frame per lane (4 lanes per channel: 16 pixels, nframes >= 5)
 
 template <typename T> struct SegTile {
     static constexpr int kPitch = kSeg * (int)sizeof(T) + 16;   // bytes per row of an I/O-dtype tile
@@ -221,12 +222,12 @@ struct SegPrepass {
     __device__ __forceinline__ void load(const T* __restrict__ g_dt, const T* __restrict__ g_cf, const T* __restrict__ g_z,
                                          bool live, int q, int t0, const Trav& tr, T* s_dt = nullptr, T* s_cf = nullptr,
                                          T* s_z = nullptr) {
-        if (kVec && tr.mode == VV_DIR_FRAMES && s_dt != nullptr && s_cf != nullptr) {
+        if (kVec && tr.mode == VV_DIR_FRAMES && s_dt != nullptr && s_cf != nullptr && frames_fits<4, kSegKP>(tr.nf, kSeg)) {
             const FramesSpan sp = frames_span(tr, t0, kSeg);
             if (live) {
-                frames_gather(s_dt, g_dt, sp, tr, q, 4);
-                frames_gather(s_cf, g_cf, sp, tr, q, 4);
-                if (g_z && s_z) frames_gather(s_z, g_z, sp, tr, q, 4);
+                frames_gather<T, 4, kSegKP>(s_dt, g_dt, sp, tr, q);        // one row at a time: 56-register kernels
+                frames_gather<T, 4, kSegKP>(s_cf, g_cf, sp, tr, q);
+                if (g_z && s_z) frames_gather<T, 4, kSegKP>(s_z, g_z, sp, tr, q);
             }
             __syncwarp();
 #pragma unroll
@@ -480,7 +481,7 @@ __global__ void __launch_bounds__(kCarryThreads) seg_carry_kernel(const float2* 
 // ================================================================ pass 3: forward outputs
 // smem: [f32 dt][f32 drive][B tile][C tile][raw u -> gated y][raw z -> pre-gate y]
 template <typename T, bool kVec, int NB>
-__global__ void __launch_bounds__(kSegThreads) seg_fwd_kernel(const vv_scan_args a) {
+__global__ void __launch_bounds__(kSegThreads, (kVec && NB <= 16) ? 7 : 4) seg_fwd_kernel(const vv_scan_args a) {
     constexpr int NQ = NB / 4;
     extern __shared__ __align__(16) unsigned char smem[];
     const int L = a.seqlen, N = a.dstate;
@@ -593,13 +594,13 @@ __global__ void __launch_bounds__(kSegThreads) seg_fwd_kernel(const vv_scan_args
         }
     }
     __syncwarp();   // the four lanes of a channel (same warp) wrote its row; each lane now flushes two chunks of it
-    if (live && kVec && c.tr.mode == VV_DIR_FRAMES) {
+    if (live && kVec && c.tr.mode == VV_DIR_FRAMES && frames_fits<4, kSegKP>(c.tr.nf, kSeg)) {
         // the rows hold the outputs in traversal order: the 4 lanes of the channel write them out run by run
         const FramesSpan sp = frames_span(c.tr, c.t0, kSeg);
-        if (a.out) frames_scatter(reinterpret_cast<T*>(a.out) + c.b * a.out_bs + d * a.out_ds,
-                                  reinterpret_cast<const T*>(t_z + r * SegTile<T>::kPitch), sp, c.tr, q, 4);
-        if (a.z) frames_scatter(reinterpret_cast<T*>(a.out_z) + c.b * a.outz_bs + d * a.outz_ds,
-                                reinterpret_cast<const T*>(t_u + r * SegTile<T>::kPitch), sp, c.tr, q, 4);
+        if (a.out) frames_scatter<T, 4, kSegKP>(reinterpret_cast<T*>(a.out) + c.b * a.out_bs + d * a.out_ds,
+                                                reinterpret_cast<const T*>(t_z + r * SegTile<T>::kPitch), sp, c.tr, q);
+        if (a.z) frames_scatter<T, 4, kSegKP>(reinterpret_cast<T*>(a.out_z) + c.b * a.outz_bs + d * a.outz_ds,
+                                              reinterpret_cast<const T*>(t_u + r * SegTile<T>::kPitch), sp, c.tr, q);
     } else if (live) {
         const unsigned char* my_u = t_u + r * SegTile<T>::kPitch;
         const unsigned char* my_z = t_z + r * SegTile<T>::kPitch;
