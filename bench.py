@@ -5,15 +5,15 @@
 
 Metric (BASELINE.json): "Mamba scan fwd+bwd GB/s vs HBM peak; Vivim clips/sec at 1/2/4/8 B200".
 
-  metric / value   selective-scan fwd+bwd algorithmic GB/s of ONE Temporal Mamba block at the Vivim stage-1 shape
-            (configs[1]: L = 5*64*64 = 20480 tokens, d_inner 128, d_state 16, bf16 I/O, fp32 state).  A block scans its
-            tokens in three directions (mamba_simple.py:217-260); here they are one launch chain (vv_scan_fwd +
-            vv_scan_bwd over three direction blocks, B / C read from x_dbl rows, z / dout shared).  A "step" = forward +
-            backward of the block's three direction scans for `clips` clips per GPU.  Algorithmic bytes = SURVEY.md
-            8(d)'s per-scan figure (fwd 4T+2S, bwd 7T+4S) x 3 scans; `bytes_compulsory_per_step` is what THIS launch has
-            to move (z and dout are read once, not three times).  Device-resident inputs, CUDA-graph replay, CUDA events
-            over exactly K steps.  `single_direction` repeats the round-1 measurement (one scan, (B,G,N,L) B / C).
-  e2e       the same block through the reference-facing plugin boundary (vivim_b200.selective_scan_cuda.fwd / .bwd, the
+  metric / value   selective-scan fwd+bwd algorithmic GB/s at the Vivim stage-1 shape (configs[1]: L = 5*64*64 = 20480
+            tokens, d_inner 128, d_state 16, bf16 I/O, fp32 state).  A "step" = forward + backward of one scan over
+            `clips` clips per GPU; algorithmic bytes = SURVEY.md 8(d): fwd 4T+2S, bwd 7T+4S.  Device-resident inputs,
+            CUDA-graph replay, CUDA events over exactly K steps.
+  block_three_directions   a Temporal Mamba block scans its tokens in three directions (mamba_simple.py:217-260); here
+            they are ONE launch chain (direction blocks with per-block traversal order, B / C read from x_dbl rows, z /
+            dout shared) -- the launch vivim_b200.mamba_block issues.  Bytes: 3 x the per-scan figure;
+            `bytes_compulsory` is what the fused launch itself has to move.
+  e2e       the headline workload through the reference-facing plugin boundary (vivim_b200.selective_scan_cuda.fwd / .bwd, the
             module that stands where the reference's pybind `selective_scan_cuda` stands; C ABI underneath) with HOST
             buffers: every step copies its inputs in from pinned host memory and all results back out.
   roofline  the dominant kernel (seg_bwd_kernel) timed alone with CUDA events.
@@ -142,8 +142,9 @@ def workload_config(clips, ndirs):
     T_in = clips * D_INNER * SEQLEN * 2
     set_bytes = (2 * ndirs + 2) * T_in + clips * ndirs * SEQLEN * (DT_RANK + 2 * D_STATE) * 2
     n_sets = max(2, -(-2 * L2_BYTES // set_bytes) + 1)
-    return {"workload": "one Temporal Mamba block: selective-scan fwd+bwd of its %d direction scan%s, Vivim stage-1 shape "
-                        "(BASELINE configs[1])" % (ndirs, "s" if ndirs > 1 else ""),
+    return {"workload": ("single Temporal Mamba block selective-scan fwd+bwd, Vivim stage-1 shape (BASELINE configs[1])" if ndirs == 1 else
+                         "one Temporal Mamba block: selective-scan fwd+bwd of its %d direction scans in one launch chain, Vivim "
+                         "stage-1 shape" % ndirs),
             "clips_per_gpu": clips, "directions": list(DIRS[:ndirs]), "seqlen": SEQLEN, "d_inner": D_INNER, "d_state": D_STATE,
             "io": "bf16", "state": "fp32",
             "l2_policy": f"rotating {n_sets} device-resident input sets ({n_sets * set_bytes / 2**20:.0f} MiB) > 126 MiB L2, "
@@ -443,23 +444,41 @@ def run_ours(args, rank, world, local_rank):
                 "note": "N=16 states per (channel, token): ~26 issue slots, 1 MUFU and 6.6 shared-memory/shuffle wavefront "
                         "bytes per state-step make this kernel issue / LSU bound, not HBM bound, on B200 (DESIGN.md section 5)"}
 
-    # ---- the round-1 workload for continuity: one direction scan per launch, (B,G,N,L) B / C
-    single = None
-    if ndirs > 1 and not args.quick:
-        s1 = [ScanSet(clips, device, seed=77 + i, ndirs=1) for i in range(workload_config(clips, 1)[1])]
-        g1 = graphs_for(s1, lib, device, torch)
+    # ---- the whole block in one launch chain: the three direction scans of Mamba.forward v3 as direction blocks of ONE
+    #      vv_scan_fwd / vv_scan_bwd (B / C from x_dbl rows, z / dout shared), what vivim_b200.mamba_block runs
+    block = None
+    if ndirs == 1 and not args.quick:
+        nb = len(DIRS)
+        sb = [ScanSet(clips, device, seed=77 + i, ndirs=nb) for i in range(workload_config(clips, nb)[1])]
+        gb = graphs_for(sb, lib, device, torch)
         for i in range(10):
-            g1[i % len(g1)].replay()
+            gb[i % len(gb)].replay()
         torch.cuda.synchronize()
         n1 = max(50, min(args.steps, 1000))
-        t1 = max_over_ranks(time_events(lambda i: g1[i % len(g1)].replay(), n1, torch), device) / n1
-        f1, b1 = algo_bytes(clips)
-        single = {"us_per_scan": t1 * 1e6, "GBps": (f1 + b1) / t1 / 1e9, "note": "one direction scan per launch chain (round-1 workload)"}
-        launches += 7 * (n1 + 10 + len(g1))
-        del s1, g1
+        tb = max_over_ranks(time_events(lambda i: gb[i % len(gb)].replay(), n1, torch), device) / n1
+        fb, bb = algo_bytes(clips * nb)
+        kb = {}
+        for bwd in (0, 1):
+            fn = lib.vv_scan_bwd if bwd else lib.vv_scan_fwd
+            for bit, name in ((1, "agg"), (2, "carry"), (4, "main")) + (((8, "cast"),) if bwd else ()):
+                for s_ in sb:
+                    s_.args.pass_mask = bit
+                run = lambda i: _lib.check(fn(ctypes.byref(sb[i % len(sb)].args), ctypes.c_void_p(stream)), "scan pass")  # noqa: E731
+                for i in range(3):
+                    run(i)
+                torch.cuda.synchronize()
+                kb[("bwd_" if bwd else "fwd_") + name] = time_events(run, reps, torch) / reps * 1e6
+        block = {"directions": list(DIRS), "us_per_block": tb * 1e6, "us_per_direction_scan": tb * 1e6 / (clips * nb),
+                 "GBps": (fb + bb) / tb / 1e9, "kernel_us": kb,
+                 "bytes_algorithmic": fb + bb, "bytes_compulsory": sum(compulsory_bytes(clips, nb)),
+                 "note": "the three direction scans of one Temporal Mamba block (mamba_simple.py:217-260) as ONE launch chain: "
+                         "direction blocks with per-block traversal order, B / C read from x_dbl rows, dB / dC written into dx_dbl, z "
+                         "and dout shared; GBps counts the reference's three calls (3 x (11T + 6S))"}
+        launches += 7 * (n1 + 10 + len(gb)) + 7 * (reps + 3)
+        del sb, gb
 
     # ---- conv1d at the same shape: all directions in one launch, and the single-direction kernels
-    conv = bench_conv(clips, ndirs, device, torch)
+    conv = bench_conv(clips, len(DIRS) if ndirs == 1 else ndirs, device, torch)
     launches += conv.pop("_launches")
 
     # ---- end to end: plugin boundary, host (pinned) buffers in, all results out, every step
@@ -508,8 +527,8 @@ def run_ours(args, rank, world, local_rank):
             "fwd_GBps_kernels_only": fwd_b / (passes["fwd_agg"] + passes["fwd_carry"] + passes["fwd_main"]) / 1e9,
             "bwd_GBps_kernels_only": bwd_b / (passes["bwd_agg"] + passes["bwd_carry"] + passes["bwd_main"] + passes["bwd_cast"]) / 1e9,
             "conv1d": conv}
-    if single:
-        line["single_direction"] = single
+    if block:
+        line["block_three_directions"] = block
     if ref_cuda:
         line["ref_cuda_us"] = ref_cuda
     line.update(vivim)
@@ -730,12 +749,14 @@ def bench_vivim(args, rank, world, device, torch, dist):
     target = torch.randint(0, 3, (batch * frames, image, image), device=device)
     model.train()
     loss_fn = RecallFocusedLoss().to(device)
-    tsg = TrainStepGraph(model, loss_fn, (clip,), (target,), autocast_dtype=torch.bfloat16)
+    overlapped = world > 1 and not args.no_overlap
+    tsg = TrainStepGraph(model, loss_fn, (clip,), (target,), autocast_dtype=torch.bfloat16,
+                         grad_allreduce=(lambda t: dist.all_reduce(t, op=dist.ReduceOp.AVG)) if overlapped else None)
     opt = torch.optim.AdamW(tsg.params, lr=1e-4, weight_decay=1e-2, betas=(0.9, 0.999), fused=True, capturable=True)
 
     def train_step():
         loss = tsg()
-        if world > 1:
+        if world > 1 and not overlapped:
             dist.all_reduce(tsg.flat_grad, op=dist.ReduceOp.AVG)
         opt.step()
         return loss
@@ -743,8 +764,13 @@ def bench_vivim(args, rank, world, device, torch, dist):
     cps, ms, loss = timed(train_step, batch)
     res.update(vivim_train_clips_per_s=cps, vivim_train_ms_per_step=ms,
                vivim_train={"batch_per_gpu": batch, "steps": steps, "loss_after": loss, "loss": "recall_focused_loss",
-                            "optimizer": "AdamW lr 1e-4 wd 1e-2 (fused)", "grad_allreduce": "one NCCL all_reduce(AVG) of the flat "
-                            "fp32 gradient (%.0f MB) after the graph replay" % (tsg.flat_grad.numel() * 4 / 1e6) if world > 1 else "none (1 GPU)",
+                            "optimizer": "AdamW lr 1e-4 wd 1e-2 (fused)",
+                            "grad_allreduce": ("none (1 GPU)" if world == 1 else
+                                               ("%d NCCL all_reduce(AVG) buckets of the flat fp32 gradient (%.0f MB) captured INSIDE the "
+                                                "graph on a side stream, each launched when the backward has produced its last gradient"
+                                                % (len(tsg._buckets), tsg.flat_grad.numel() * 4 / 1e6)) if overlapped else
+                                               "one NCCL all_reduce(AVG) of the flat fp32 gradient (%.0f MB) after the graph replay"
+                                               % (tsg.flat_grad.numel() * 4 / 1e6)),
                             "launch": "forward + backward as one CUDA graph (vivim_b200.graphed.TrainStepGraph)"})
     del tsg, opt
     # ---- inference (configs[3]: 32 clips over 8 GPUs -> 4 per GPU)
@@ -770,10 +796,14 @@ def main():
     ap.add_argument("--warmup", type=int, default=None)
     ap.add_argument("--impl", choices=("ours", "reference"), default="ours")
     ap.add_argument("--clips", type=int, default=1, help="clips per GPU (BASELINE configs[1]: 1)")
-    ap.add_argument("--dirs", type=int, default=3, choices=(1, 2, 3), help="direction scans per block (Vivim's v3: 3)")
+    ap.add_argument("--dirs", type=int, default=1, choices=(1, 2, 3),
+                    help="direction scans per launch chain of the headline workload (1 = BASELINE configs[1], one scan over "
+                         "d_inner 128; 3 = the block's three directions fused, also reported as block_three_directions)")
     ap.add_argument("--dir-modes", default=None, help="kernel development: comma list overriding the traversal order of the "
                                                       "direction blocks, e.g. fwd,fwd,fwd")
     ap.add_argument("--no-vivim", action="store_true", help="skip the whole-network clips/s legs")
+    ap.add_argument("--no-overlap", action="store_true", help="training: one all-reduce after the graph replay instead of "
+                                                              "bucketed all-reduces captured inside the graph")
     ap.add_argument("--quick", action="store_true", help="kernel development: skip the slow side measurements")
     args = ap.parse_args()
     if args.dir_modes:

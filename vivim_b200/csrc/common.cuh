@@ -406,6 +406,9 @@ __device__ __forceinline__ float softplus_f(float v) {
 // scheduled as soon as every CTA of this grid has been scheduled and called it; pdl_wait() blocks
 // until the predecessor grid has completed and its memory is visible.  Both are no-ops for a
 // kernel launched without the attribute / without a PDL successor.
+// L2 prefetch of the cache line holding `p`: a hint without architectural effect, so it may run ahead of pdl_wait() on
+// tensors the predecessor kernel may still be writing (the later real load reads whatever L2 holds then).
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 

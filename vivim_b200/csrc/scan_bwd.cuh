@@ -74,8 +74,9 @@ struct BwdTileLoader {
     Raw8<T, kVec> raw[kPer];
     StateQuad<T> quad[kPerQ];
     bool rows;   // see StateTileLoader (scan_seq.cuh): `rows` = (.., N, L) layout walked left to right, else (position, 4 states) items
-    __device__ __forceinline__ void load(const T* __restrict__ base, int64_t ns, int64_t ls, int N, int t0, const Trav& tr) {
-        rows = ls <= 1 && tr.mode == VV_DIR_FWD;
+    __device__ __forceinline__ void load(const T* __restrict__ base, int64_t ns, int64_t ls, int N, int t0, const Trav& tr,
+                                         bool gen = true) {
+        rows = !gen || (ls <= 1 && tr.mode == VV_DIR_FWD);
         if (rows) {
 #pragma unroll
             for (int j = 0; j < kPer; ++j) {
@@ -132,7 +133,7 @@ struct BwdTileLoader {
 //   du = D g + dt sum_n r B            ddt = u sum_n r B + sum_n A_n w
 //   dA_n = sum_t dt w                  dB_n = sum_d r dt u          dC_n = sum_d g h
 // NB: compile-time state block (8, 16, 32) >= N; rows N..NB-1 are zero padding.
-template <typename T, bool kVec, int NB>
+template <typename T, bool kVec, int NB, bool kGen>
 __global__ void __launch_bounds__(kBwdThreads, 4) seg_bwd_kernel(const vv_scan_args a) {
     extern __shared__ float4 smem4[];
     const int L = a.seqlen, N = a.dstate;
@@ -159,13 +160,13 @@ __global__ void __launch_bounds__(kBwdThreads, 4) seg_bwd_kernel(const vv_scan_a
     const int S = gridDim.x;
     const int t0s = seg * kSeg;
     const int t0 = live ? t0s + tb * 8 : L;   // dead channels read as padding
-    const Trav tr = group_trav(a, grp);       // t0 / t0s are TRAVERSAL positions of the direction block
-    const int dg = gate_row(a, d);
+    const Trav tr = group_trav<kGen>(a, grp);   // t0 / t0s are TRAVERSAL positions of the direction block
+    const int dg = gate_row<kGen>(a, d);
 
     // ---- every global load that does not depend on the preceding kernels, issued up front
     Raw8<T, kVec> r_dt, r_u, r_g, r_z;
     constexpr int kKP = 3;                                    // FRAMES staging: 8 lanes x 3 pixels of a frame (nframes >= 3)
-    const bool staged = kVec && tr.mode == VV_DIR_FRAMES && frames_fits<8, kKP>(tr.nf, kSeg);   // rows gathered run by run through shared memory
+    const bool staged = kGen && kVec && tr.mode == VV_DIR_FRAMES && frames_fits<8, kKP>(tr.nf, kSeg);   // rows gathered run by run through shared memory
     const FramesSpan span = frames_span(tr, t0s, kSeg);
     if (staged) {
         // staging rows of the warp's 4 channels x 4 tensors: the warp's own dB / dC tile, not used before the state loop
@@ -190,8 +191,8 @@ __global__ void __launch_bounds__(kBwdThreads, 4) seg_bwd_kernel(const vv_scan_a
         if (a.z) r_z.load_trav(reinterpret_cast<const T*>(a.z) + b * a.z_bs + dg * a.z_ds, t0, tr);
     }
     BwdTileLoader<T, kVec, NB> lB, lC;
-    lB.load(reinterpret_cast<const T*>(a.Bm) + b * a.B_bs + grp * a.B_gs, a.B_ns, a.B_ls, N, t0s, tr);
-    lC.load(reinterpret_cast<const T*>(a.Cm) + b * a.C_bs + grp * a.C_gs, a.C_ns, a.C_ls, N, t0s, tr);
+    lB.load(reinterpret_cast<const T*>(a.Bm) + b * a.B_bs + grp * a.B_gs, a.B_ns, a.B_ls, N, t0s, tr, kGen);
+    lC.load(reinterpret_cast<const T*>(a.Cm) + b * a.C_bs + grp * a.C_gs, a.C_ns, a.C_ls, N, t0s, tr, kGen);
     const float bias = a.delta_bias ? a.delta_bias[d] : 0.f;
     const float Dv = a.D ? a.D[d] : 0.f;
     const bool sp = a.delta_softplus != 0;
@@ -530,7 +531,7 @@ __global__ void __launch_bounds__(kCastThreads) cast_bc_strided_kernel(const vv_
     const int seg = blockIdx.x, g = blockIdx.y, b = blockIdx.z;
     const int t0 = seg * kSeg;
     const int tid = threadIdx.x;
-    const Trav tr = group_trav(a, g);
+    const Trav tr = group_trav<true>(a, g);
     const int64_t acc_base = (((int64_t)b * a.ngroups + g) * N) * L;
     if (tid < kSeg) s_mem[tid] = t0 + tid < L ? tr.mem(t0 + tid) : -1;
     {   // rows of the accumulators: thread = (row n0 + 4 i, position j), 64 consecutive floats per row

@@ -132,8 +132,9 @@ struct StateTileLoader {
     Raw8<T, kVec> raw[kPer];
     StateQuad<T> quad[kPerQ];
     bool rows;
-    __device__ __forceinline__ void load(const T* __restrict__ base, int64_t ns, int64_t ls, int N, int t0, const Trav& tr) {
-        rows = ls <= 1 && tr.mode == VV_DIR_FWD;
+    __device__ __forceinline__ void load(const T* __restrict__ base, int64_t ns, int64_t ls, int N, int t0, const Trav& tr,
+                                         bool gen = true) {
+        rows = !gen || (ls <= 1 && tr.mode == VV_DIR_FWD);
         if (rows) {
 #pragma unroll
             for (int j = 0; j < kPer; ++j) {
@@ -178,9 +179,19 @@ struct SegCoord {
     Trav tr;                        // traversal order of the CTA's direction block
 };
 
-// traversal order of group g (groups are split evenly over the direction blocks)
+// traversal order of group g (groups are split evenly over the direction blocks).  kGen = false: the launch is the
+// plain reference op (one left-to-right direction, (.., N, L) B / C, no shared gate rows) -- everything below folds to
+// constants and the kernels compile to the lean single-direction code.
+template <bool kGen>
 __device__ __forceinline__ Trav group_trav(const vv_scan_args& a, int g) {
     Trav tr;
+    if (!kGen) {
+        tr.mode = VV_DIR_FWD;
+        tr.L = a.seqlen;
+        tr.nf = 1;
+        tr.hw = a.seqlen;
+        return tr;
+    }
     const int ndirs = a.ndirs > 1 ? a.ndirs : 1;
     tr.mode = a.dir_mode[g / (a.ngroups / ndirs)];
     tr.L = a.seqlen;
@@ -190,8 +201,10 @@ __device__ __forceinline__ Trav group_trav(const vv_scan_args& a, int g) {
 }
 
 // channel row of the tensors shared by the direction blocks (z, dout)
-__device__ __forceinline__ int gate_row(const vv_scan_args& a, int d) { return a.gate_rows > 0 ? d % a.gate_rows : d; }
+template <bool kGen>
+__device__ __forceinline__ int gate_row(const vv_scan_args& a, int d) { return (kGen && a.gate_rows > 0) ? d % a.gate_rows : d; }
 
+template <bool kGen>
 __device__ __forceinline__ SegCoord seg_coord(const vv_scan_args& a) {
     SegCoord c;
     const int dpg = a.dim / a.ngroups;
@@ -203,7 +216,7 @@ __device__ __forceinline__ SegCoord seg_coord(const vv_scan_args& a) {
     const int off = (blockIdx.y - c.g * blocks_per_group) * kSegRows;
     c.d0 = c.g * dpg + off;
     c.nrows = min(kSegRows, dpg - off);
-    c.tr = group_trav(a, c.g);
+    c.tr = group_trav<kGen>(a, c.g);
     return c;
 }
 
@@ -292,12 +305,12 @@ struct SegPrepass {
 //               the neighbouring segment.
 // Register budget: the 128-bit variants with <= 16 states fit 56 registers (9 CTAs / SM: one wave at the B = 1 stage-1
 // shape); the element-wise, fp32 and 32-state variants would spill there and get 96.
-template <typename T, bool kVec, int NB, bool kRev>
+template <typename T, bool kVec, int NB, bool kRev, bool kGen>
 __global__ void __launch_bounds__(kSegThreads, (kVec && NB <= 16 && sizeof(T) == 2) ? 9 : 5) seg_agg_kernel(const vv_scan_args a) {
     constexpr int NQ = NB / 4;
     extern __shared__ __align__(16) unsigned char smem[];
     const int L = a.seqlen, N = a.dstate;
-    const SegCoord c = seg_coord(a);
+    const SegCoord c = seg_coord<kGen>(a);
     unsigned char* f_dt = smem;
     unsigned char* f_cf = f_dt + kSegRows * kF32Pitch;
     float* t_m = reinterpret_cast<float*>(f_cf + kSegRows * kF32Pitch);
@@ -305,16 +318,29 @@ __global__ void __launch_bounds__(kSegThreads, (kVec && NB <= 16 && sizeof(T) ==
     // (a GEMM, a conv, another scan) and may itself have released its dependents early, so nothing the caller provides
     // -- inputs AND parameters -- is read before the predecessor has completed.  Only index arithmetic runs ahead.  The
     // dependents (carry, main) are released after that point, so their own pre-wait loads are safe as well.
-    pdl_wait();
-    pdl_trigger();
-
     const int r = threadIdx.x >> 2, q = threadIdx.x & 3;
     const bool live = r < c.nrows;
     const int d = c.d0 + (live ? r : 0);
-    const int dg = gate_row(a, d);
+    const int dg = gate_row<kGen>(a, d);
+    const T* g_dt = reinterpret_cast<const T*>(a.delta) + c.b * a.delta_bs + d * a.delta_ds;
+    // While the predecessor drains: pull this CTA's rows towards L2 (hints only, see prefetch_l2).  One lane per channel
+    // covers the 64-position row segment (one or two 128-byte lines); FRAMES rows are not contiguous and are skipped.
+    if (live && q == 0 && c.tr.mode != VV_DIR_FRAMES && c.t0 < L) {
+        const int m0 = c.tr.mode == VV_DIR_REV ? max(L - kSeg - c.t0, 0) : c.t0;
+        const T* g_cf0 = kRev ? reinterpret_cast<const T*>(a.dout) + c.b * a.dout_bs + dg * a.dout_ds
+                              : reinterpret_cast<const T*>(a.u) + c.b * a.u_bs + d * a.u_ds;
+#pragma unroll
+        for (int h = 0; h < (int)sizeof(T) / 2; ++h) {
+            prefetch_l2(g_dt + m0 + h * (kSeg / 2));
+            prefetch_l2(g_cf0 + m0 + h * (kSeg / 2));
+            if (kRev && a.z) prefetch_l2(reinterpret_cast<const T*>(a.z) + c.b * a.z_bs + dg * a.z_ds + m0 + h * (kSeg / 2));
+        }
+    }
+    pdl_wait();
+    pdl_trigger();
+
     const float bias = a.delta_bias ? a.delta_bias[d] : 0.f;
     const bool sp = a.delta_softplus != 0;
-    const T* g_dt = reinterpret_cast<const T*>(a.delta) + c.b * a.delta_bs + d * a.delta_ds;
     // every global load of the CTA is issued before the first use, so the latencies overlap
     SegPrepass<T, kVec, kRev ? 1 : 0> pre;
     StateTileLoader<T, kVec, NB> st;
@@ -325,11 +351,11 @@ __global__ void __launch_bounds__(kSegThreads, (kVec && NB <= 16 && sizeof(T) ==
     T* s_z = sizeof(T) == 2 ? s_dt + kSeg : nullptr;
     if (!kRev) {
         pre.load(g_dt, reinterpret_cast<const T*>(a.u) + c.b * a.u_bs + d * a.u_ds, nullptr, live, q, c.t0, c.tr, s_dt, s_cf, s_z);
-        st.load(reinterpret_cast<const T*>(a.Bm) + c.b * a.B_bs + c.g * a.B_gs, a.B_ns, a.B_ls, N, c.t0, c.tr);
+        st.load(reinterpret_cast<const T*>(a.Bm) + c.b * a.B_bs + c.g * a.B_gs, a.B_ns, a.B_ls, N, c.t0, c.tr, kGen);
     } else {
         pre.load(g_dt, reinterpret_cast<const T*>(a.dout) + c.b * a.dout_bs + dg * a.dout_ds,
                  a.z ? reinterpret_cast<const T*>(a.z) + c.b * a.z_bs + dg * a.z_ds : nullptr, live, q, c.t0, c.tr, s_dt, s_cf, s_z);
-        st.load(reinterpret_cast<const T*>(a.Cm) + c.b * a.C_bs + c.g * a.C_gs, a.C_ns, a.C_ls, N, c.t0, c.tr);
+        st.load(reinterpret_cast<const T*>(a.Cm) + c.b * a.C_bs + c.g * a.C_gs, a.C_ns, a.C_ls, N, c.t0, c.tr, kGen);
     }
     float A2[NQ], h[NQ];
 #pragma unroll
@@ -480,12 +506,12 @@ __global__ void __launch_bounds__(kCarryThreads) seg_carry_kernel(const float2* 
 
 // ================================================================ pass 3: forward outputs
 // smem: [f32 dt][f32 drive][B tile][C tile][raw u -> gated y][raw z -> pre-gate y]
-template <typename T, bool kVec, int NB>
+template <typename T, bool kVec, int NB, bool kGen>
 __global__ void __launch_bounds__(kSegThreads, (kVec && NB <= 16) ? 7 : 4) seg_fwd_kernel(const vv_scan_args a) {
     constexpr int NQ = NB / 4;
     extern __shared__ __align__(16) unsigned char smem[];
     const int L = a.seqlen, N = a.dstate;
-    const SegCoord c = seg_coord(a);
+    const SegCoord c = seg_coord<kGen>(a);
     unsigned char* f_dt = smem;
     unsigned char* f_dr = f_dt + kSegRows * kF32Pitch;
     float* t_B = reinterpret_cast<float*>(f_dr + kSegRows * kF32Pitch);
@@ -505,11 +531,11 @@ __global__ void __launch_bounds__(kSegThreads, (kVec && NB <= 16) ? 7 : 4) seg_f
     StateTileLoader<T, kVec, NB> stB, stC;
     pre.load(reinterpret_cast<const T*>(a.delta) + c.b * a.delta_bs + d * a.delta_ds,
              reinterpret_cast<const T*>(a.u) + c.b * a.u_bs + d * a.u_ds,
-             a.z ? reinterpret_cast<const T*>(a.z) + c.b * a.z_bs + gate_row(a, d) * a.z_ds : nullptr, live, q, c.t0, c.tr,
+             a.z ? reinterpret_cast<const T*>(a.z) + c.b * a.z_bs + gate_row<kGen>(a, d) * a.z_ds : nullptr, live, q, c.t0, c.tr,
              reinterpret_cast<T*>(f_dt + r * kF32Pitch), reinterpret_cast<T*>(t_u + r * SegTile<T>::kPitch),
              reinterpret_cast<T*>(t_z + r * SegTile<T>::kPitch));
-    stB.load(reinterpret_cast<const T*>(a.Bm) + c.b * a.B_bs + c.g * a.B_gs, a.B_ns, a.B_ls, N, c.t0, c.tr);
-    stC.load(reinterpret_cast<const T*>(a.Cm) + c.b * a.C_bs + c.g * a.C_gs, a.C_ns, a.C_ls, N, c.t0, c.tr);
+    stB.load(reinterpret_cast<const T*>(a.Bm) + c.b * a.B_bs + c.g * a.B_gs, a.B_ns, a.B_ls, N, c.t0, c.tr, kGen);
+    stC.load(reinterpret_cast<const T*>(a.Cm) + c.b * a.C_bs + c.g * a.C_gs, a.C_ns, a.C_ls, N, c.t0, c.tr, kGen);
     float A2[NQ], h[NQ];
 #pragma unroll
     for (int k = 0; k < NQ; ++k) {

@@ -387,12 +387,18 @@ SegPlan plan_seg(const vv_scan_args& a) {
     return p;
 }
 
+// the launch is the plain reference op: one left-to-right direction, (.., N, L) B / C, no shared gate rows
+bool plain_scan(const vv_scan_args& a) {
+    return all_forward(a) && a.B_ls <= 1 && a.C_ls <= 1 && a.gate_rows == 0;
+}
+
 template <typename T, bool kVec, int NB, bool kRev>
 int launch_seg_agg(const vv_scan_args& a, const SegPlan& p, cudaStream_t st) {
     const size_t smem = 2 * (size_t)vv::kSegRows * vv::kF32Pitch + (size_t)vv::kSeg * NB * sizeof(float);
     int rc;
-    if ((rc = set_smem(vv::seg_agg_kernel<T, kVec, NB, kRev>, smem)) != VV_OK) return rc;
-    launch_kernel(vv::seg_agg_kernel<T, kVec, NB, kRev>, p.grid, dim3(vv::kSegThreads), smem, st, use_pdl(), a);
+    auto kernel = plain_scan(a) ? vv::seg_agg_kernel<T, kVec, NB, kRev, false> : vv::seg_agg_kernel<T, kVec, NB, kRev, true>;
+    if ((rc = set_smem(kernel, smem)) != VV_OK) return rc;
+    launch_kernel(kernel, p.grid, dim3(vv::kSegThreads), smem, st, use_pdl(), a);
     return check_launch(kRev ? "seg_agg_kernel<rev>" : "seg_agg_kernel<fwd>");
 }
 
@@ -401,8 +407,9 @@ int launch_seg_fwd(const vv_scan_args& a, const SegPlan& p, cudaStream_t st) {
     const size_t smem = 2 * (size_t)vv::kSegRows * vv::kF32Pitch + 2 * (size_t)vv::kSeg * NB * sizeof(float) +
                         2 * (size_t)vv::kSegRows * vv::SegTile<T>::kPitch;
     int rc;
-    if ((rc = set_smem(vv::seg_fwd_kernel<T, kVec, NB>, smem)) != VV_OK) return rc;
-    launch_kernel(vv::seg_fwd_kernel<T, kVec, NB>, p.grid, dim3(vv::kSegThreads), smem, st, use_pdl() && (pass_mask(a) & 2), a);
+    auto kernel = plain_scan(a) ? vv::seg_fwd_kernel<T, kVec, NB, false> : vv::seg_fwd_kernel<T, kVec, NB, true>;
+    if ((rc = set_smem(kernel, smem)) != VV_OK) return rc;
+    launch_kernel(kernel, p.grid, dim3(vv::kSegThreads), smem, st, use_pdl() && (pass_mask(a) & 2), a);
     return check_launch("seg_fwd_kernel");
 }
 
@@ -459,9 +466,9 @@ int scan_bwd_t(const vv_scan_args& a, cudaStream_t st) {
         const dim3 grid(sp.segs, a.ngroups * ((dpg + vv::kBwdRows - 1) / vv::kBwdRows), a.batch);
         VV_NB_SWITCH(sp.NB, {
             const size_t smem = vv::bwd_smem_bytes(NB);
-            if ((rc = set_smem(vv::seg_bwd_kernel<T, kVec, NB>, smem)) != VV_OK) return rc;
-            launch_kernel(vv::seg_bwd_kernel<T, kVec, NB>, grid, dim3(vv::kBwdThreads), smem, st,
-                          use_pdl() && (pass_mask(a) & 2), a);
+            auto kernel = plain_scan(a) ? vv::seg_bwd_kernel<T, kVec, NB, false> : vv::seg_bwd_kernel<T, kVec, NB, true>;
+            if ((rc = set_smem(kernel, smem)) != VV_OK) return rc;
+            launch_kernel(kernel, grid, dim3(vv::kBwdThreads), smem, st, use_pdl() && (pass_mask(a) & 2), a);
         });
         if ((rc = check_launch("seg_bwd_kernel")) != VV_OK) return rc;
     }

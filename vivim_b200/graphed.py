@@ -54,21 +54,29 @@ class TrainStepGraph:
     clip 5) on B200: 94 ms eager -> 49 ms per step, and 7.49x on 8 GPUs where per-rank launch overhead had limited
     DDP to 6.0x (profiles/r01_vivim_step.md).
 
-        step = TrainStepGraph(model, loss_fn, (clip,), (target,), autocast_dtype=torch.bfloat16)
+        step = TrainStepGraph(model, loss_fn, (clip,), (target,), autocast_dtype=torch.bfloat16,
+                              grad_allreduce=(lambda t: dist.all_reduce(t, op=dist.ReduceOp.AVG)) if world > 1 else None)
         opt = torch.optim.AdamW(step.params, lr=1e-4, fused=True, capturable=True)
         for clip_batch, target_batch in loader:
-            loss = step(clip_batch, target_batch)          # copies into the static inputs, replays
-            if world > 1: dist.all_reduce(step.flat_grad, op=dist.ReduceOp.AVG)
+            loss = step(clip_batch, target_batch)          # copies into the static inputs, replays (gradients arrive averaged)
             opt.step()
 
     The model must be capture-safe (static shapes, no host synchronisation in forward/backward); everything in this
     repo is.  ``loss_fn(output, *targets)`` must return a scalar tensor.
     """
 
-    def __init__(self, model: nn.Module, loss_fn, inputs, targets=(), autocast_dtype=None, warmup_iters: int = 3):
+    def __init__(self, model: nn.Module, loss_fn, inputs, targets=(), autocast_dtype=None, warmup_iters: int = 3,
+                 grad_allreduce=None, bucket_mb: float = 32.0):
+        """``grad_allreduce``: optional ``fn(tensor)`` that all-reduces a slice of ``flat_grad`` in place (e.g.
+        ``lambda t: dist.all_reduce(t, op=dist.ReduceOp.AVG)``).  When given, the gradient buffer is cut into buckets of
+        about ``bucket_mb`` MB in parameter order and each bucket is reduced INSIDE the graph, on a side stream, as soon
+        as the backward has produced its last gradient -- the collective of the late layers overlaps the backward of the
+        early ones (what DDP's bucketing does, but captured: no per-step Python, no hooks at replay time).  Without it the
+        caller reduces ``flat_grad`` after the replay."""
         if not torch.cuda.is_available():
             raise RuntimeError("TrainStepGraph needs a CUDA device")
         self.model, self.loss_fn, self.autocast_dtype = model, loss_fn, autocast_dtype
+        self.grad_allreduce = grad_allreduce
         self.inputs = tuple(t.clone() for t in inputs)
         self.targets = tuple(t.clone() for t in targets)
         self.params = [p for p in model.parameters() if p.requires_grad]
@@ -81,6 +89,23 @@ class TrainStepGraph:
             p.grad = self.flat_grad[off:off + p.numel()].view_as(p)
             off += p.numel()
         self.loss = torch.zeros((), device=device)
+        self._buckets, self._in_step = [], False
+        if grad_allreduce is not None:
+            self.comm_stream = torch.cuda.Stream(device)
+            limit = int(bucket_mb * 1e6 / 4)
+            lo = off = 0
+            owner = []
+            for p in self.params:
+                owner.append(len(self._buckets))
+                off += p.numel()
+                if off - lo >= limit:
+                    self._buckets.append((lo, off))
+                    lo = off
+            if off > lo:
+                self._buckets.append((lo, off))
+            self._bucket_params = [owner.count(b) for b in range(len(self._buckets))]
+            for p, b in zip(self.params, owner):
+                p.register_post_accumulate_grad_hook(lambda _p, b=b: self._grad_ready(b))
         side = torch.cuda.Stream(device)
         side.wait_stream(torch.cuda.current_stream(device))
         with torch.cuda.stream(side):
@@ -92,8 +117,25 @@ class TrainStepGraph:
         with torch.cuda.graph(self.graph):
             self._fwd_bwd()
 
+    def _grad_ready(self, b):
+        if not self._in_step:
+            return
+        self._pending[b] -= 1
+        if self._pending[b] == 0:
+            self._reduce_bucket(b)
+
+    def _reduce_bucket(self, b):
+        lo, hi = self._buckets[b]
+        self.comm_stream.wait_stream(torch.cuda.current_stream())     # fork: the bucket's gradients are complete
+        with torch.cuda.stream(self.comm_stream):
+            self.grad_allreduce(self.flat_grad[lo:hi])
+        self._pending[b] = -1
+
     def _fwd_bwd(self):
         self.flat_grad.zero_()
+        if self._buckets:
+            self._pending = list(self._bucket_params)
+            self._in_step = True
         if self.autocast_dtype is not None:
             with torch.autocast("cuda", dtype=self.autocast_dtype, cache_enabled=False):
                 out = self.model(*self.inputs)
@@ -101,6 +143,12 @@ class TrainStepGraph:
             out = self.model(*self.inputs)
         loss = self.loss_fn(out, *self.targets)
         loss.backward()
+        if self._buckets:
+            self._in_step = False
+            for b in range(len(self._buckets) - 1, -1, -1):            # parameters that received no gradient this step
+                if self._pending[b] >= 0:
+                    self._reduce_bucket(b)
+            torch.cuda.current_stream().wait_stream(self.comm_stream)    # join
         self.loss.copy_(loss.detach())
 
     def __call__(self, *batch):
