@@ -743,6 +743,11 @@ def bench_vivim(args, rank, world, device, torch, dist):
     for name, p in model.named_parameters():        # unused by the forward, as in the reference
         if "downsample_layers.layer_norm" in name or "decoder.classifier" in name:
             p.requires_grad_(False)
+    n_ln = 0
+    if not args.torch_layernorm:
+        # the LayerNorm kernels written for the Temporal Mamba blocks also serve the SegFormer stages' nn.LayerNorm modules
+        from vivim_b200.layernorm import use_token_layernorm
+        n_ln = use_token_layernorm(model)
     # ---- training (configs[2])
     batch = 3
     clip = torch.randn(batch, frames, 3, image, image, device=device)
@@ -782,6 +787,8 @@ def bench_vivim(args, rank, world, device, torch, dist):
     res.update(vivim_infer_clips_per_s=cps, vivim_infer_ms_per_step=ms,
                vivim_infer={"batch_per_gpu": batch, "steps": steps, "launch": "forward as one CUDA graph (InferenceGraph)"})
     res["vivim_config"] = {"workload": "Vivim multiclass, image 256, clip_length 5, 3 classes, random init, synthetic clips, bf16 autocast",
+                           "layernorm": ("vivim_b200 TokenLayerNorm in the Temporal Mamba blocks and, re-classed in place, in %d SegFormer "
+                                         "nn.LayerNorm modules" % n_ln) if n_ln else "vivim_b200 TokenLayerNorm in the Temporal Mamba blocks only",
                            "model": "vivim_b200.temporal_model.Vivim (restates modeling/vivim.py; state-dict compatible)"}
     res["_launches"] = launches
     del infer, model
@@ -802,6 +809,7 @@ def main():
     ap.add_argument("--dir-modes", default=None, help="kernel development: comma list overriding the traversal order of the "
                                                       "direction blocks, e.g. fwd,fwd,fwd")
     ap.add_argument("--no-vivim", action="store_true", help="skip the whole-network clips/s legs")
+    ap.add_argument("--torch-layernorm", action="store_true", help="keep torch's LayerNorm in the SegFormer stages")
     ap.add_argument("--no-overlap", action="store_true", help="training: one all-reduce after the graph replay instead of "
                                                               "bucketed all-reduces captured inside the graph")
     ap.add_argument("--quick", action="store_true", help="kernel development: skip the slow side measurements")

@@ -212,6 +212,32 @@ typedef struct {
 int vv_dwconv3d_fwd(const vv_dwconv3d_args *a, void *stream);
 int vv_dwconv3d_bwd(const vv_dwconv3d_args *a, void *stream);
 
+/* ------------------------------------------------------------------ LayerNorm over the channels of token tensors
+ * The glue around the Mamba path in a Temporal Mamba block (modeling/vivim.py:153-157: norm1 / norm2 are nn.LayerNorm
+ * over (B, tokens, C)): y = (x - mean) * rstd * weight + bias per row, eps inside the square root.  x is (rows, C) with
+ * unit channel stride; `out` may be written in another dtype than x (e.g. bf16 for the GEMM that follows under
+ * autocast).  C <= 512.  Backward: dx (dtype of x), dweight / dbias accumulated in fp32 (+=, zeroed by the caller).
+ */
+typedef struct {
+    const void *x;        /* (rows, C) io_dtype, row stride x_rs */
+    const float *weight;  /* (C) float32 or NULL (= 1) */
+    const float *bias;    /* (C) float32 or NULL (= 0) */
+    void *out;            /* fwd: (rows, C) out_dtype, row stride out_rs */
+    float *mean, *rstd;   /* (rows) float32: written by fwd, read by bwd */
+    const void *dout;     /* bwd: (rows, C) out_dtype, row stride dout_rs */
+    void *dx;             /* bwd: (rows, C) io_dtype, row stride dx_rs, or NULL */
+    float *dweight;       /* bwd: (C) float32 +=, or NULL */
+    float *dbias;         /* bwd: (C) float32 +=, or NULL */
+    int64_t rows;
+    int32_t channels;
+    int64_t x_rs, out_rs, dout_rs, dx_rs;
+    int32_t io_dtype, out_dtype; /* VV_F32 / VV_F16 / VV_BF16; out_dtype == io_dtype, or io_dtype == VV_F32 */
+    float eps;
+} vv_layernorm_args;
+
+int vv_layernorm_fwd(const vv_layernorm_args *a, void *stream);
+int vv_layernorm_bwd(const vv_layernorm_args *a, void *stream);
+
 /* number of kernel launches the last successful call on this thread enqueued (for bench.py) */
 int vv_last_launch_count(void);
 

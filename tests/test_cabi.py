@@ -36,7 +36,8 @@ def test_exports_every_declared_symbol(L):
 def test_struct_layout_matches_c(tmp_path):
     """sizeof and the offset of EVERY field of every args struct, compiled from the header with gcc."""
     structs = {"vv_scan_args": _lib.ScanArgs, "vv_conv1d_args": _lib.ConvArgs,
-               "vv_conv1d_dirs_args": _lib.ConvDirsArgs, "vv_dwconv3d_args": _lib.DwConv3dArgs}
+               "vv_conv1d_dirs_args": _lib.ConvDirsArgs, "vv_dwconv3d_args": _lib.DwConv3dArgs,
+               "vv_layernorm_args": _lib.LayerNormArgs}
     lines = []
     for cname, cls in structs.items():
         lines.append(f'printf("%zu\\n", sizeof({cname}));')

@@ -4,7 +4,7 @@ from __future__ import annotations
 
 import ctypes
 import os
-from ctypes import POINTER, Structure, c_char_p, c_int, c_int32, c_int64, c_void_p
+from ctypes import POINTER, Structure, c_char_p, c_float, c_int, c_int32, c_int64, c_void_p
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "lib", "libvivim_b200.so")
@@ -80,10 +80,22 @@ class DwConv3dArgs(Structure):
     ]
 
 
+class LayerNormArgs(Structure):
+    """vv_layernorm_args"""
+    _fields_ = [
+        ("x", c_void_p), ("weight", c_void_p), ("bias", c_void_p), ("out", c_void_p),
+        ("mean", c_void_p), ("rstd", c_void_p), ("dout", c_void_p), ("dx", c_void_p),
+        ("dweight", c_void_p), ("dbias", c_void_p),
+        ("rows", c_int64), ("channels", c_int32),
+        ("x_rs", c_int64), ("out_rs", c_int64), ("dout_rs", c_int64), ("dx_rs", c_int64),
+        ("io_dtype", c_int32), ("out_dtype", c_int32), ("eps", c_float),
+    ]
+
+
 # every symbol include/vivim_b200.h declares (checked by tests/test_cabi.py)
 EXPORTS = ("vv_version", "vv_last_error", "vv_scan_num_segments", "vv_conv1d_fwd", "vv_conv1d_bwd",
            "vv_conv1d_dirs_fwd", "vv_conv1d_dirs_bwd", "vv_scan_fwd", "vv_scan_bwd", "vv_last_launch_count",
-           "vv_debug_force_scalar_io", "vv_dwconv3d_fwd", "vv_dwconv3d_bwd")
+           "vv_debug_force_scalar_io", "vv_dwconv3d_fwd", "vv_dwconv3d_bwd", "vv_layernorm_fwd", "vv_layernorm_bwd")
 
 _lib = None
 
@@ -106,7 +118,8 @@ def lib() -> ctypes.CDLL:
         for name, argt in (("vv_conv1d_fwd", ConvArgs), ("vv_conv1d_bwd", ConvArgs),
                            ("vv_conv1d_dirs_fwd", ConvDirsArgs), ("vv_conv1d_dirs_bwd", ConvDirsArgs),
                            ("vv_scan_fwd", ScanArgs), ("vv_scan_bwd", ScanArgs),
-                           ("vv_dwconv3d_fwd", DwConv3dArgs), ("vv_dwconv3d_bwd", DwConv3dArgs)):
+                           ("vv_dwconv3d_fwd", DwConv3dArgs), ("vv_dwconv3d_bwd", DwConv3dArgs),
+                           ("vv_layernorm_fwd", LayerNormArgs), ("vv_layernorm_bwd", LayerNormArgs)):
             fn = getattr(L, name)
             fn.argtypes = [POINTER(argt), c_void_p]
             fn.restype = c_int

@@ -422,6 +422,7 @@ template <typename T> __device__ __forceinline__ float2 unpack_pair(uint32_t w);
 template <> __device__ __forceinline__ float2 unpack_pair<__nv_bfloat16>(uint32_t w) {
     return make_float2(__uint_as_float(w << 16), __uint_as_float(w & 0xffff0000u));
 }
+template <> __device__ __forceinline__ float2 unpack_pair<float>(uint32_t w) { return make_float2(__uint_as_float(w), 0.f); }   // never used
 template <> __device__ __forceinline__ float2 unpack_pair<__half>(uint32_t w) {
     return __half22float2(*reinterpret_cast<const __half2*>(&w));
 }

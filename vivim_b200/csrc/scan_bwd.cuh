@@ -165,25 +165,18 @@ __global__ void __launch_bounds__(kBwdThreads, 4) seg_bwd_kernel(const vv_scan_a
 
     // ---- every global load that does not depend on the preceding kernels, issued up front
     Raw8<T, kVec> r_dt, r_u, r_g, r_z;
-    constexpr int kKP = 3;                                    // FRAMES staging: 8 lanes x 3 pixels of a frame (nframes >= 3)
-    const bool staged = kGen && kVec && tr.mode == VV_DIR_FRAMES && frames_fits<8, kKP>(tr.nf, kSeg);   // rows gathered run by run through shared memory
+    constexpr int kKP = 3, kNF = 5;                           // FRAMES staging: 8 lanes x 3 pixels of a frame, nframes <= 5
+    // FRAMES order: rows gathered run by run through shared memory (all loads in flight before the first store)
+    const bool staged = kGen && kVec && tr.mode == VV_DIR_FRAMES && tr.nf <= kNF && frames_fits<8, kKP>(tr.nf, kSeg);
     const FramesSpan span = frames_span(tr, t0s, kSeg);
+    FramesGather<T, 8, kKP, kNF> fg_dt, fg_u, fg_g, fg_z;
     if (staged) {
-        // staging rows of the warp's 4 channels x 4 tensors: the warp's own dB / dC tile, not used before the state loop
-        T* stg = reinterpret_cast<T*>(tdB) + cg * kSeg;
         if (live) {
-            frames_gather2<T, 8, kKP>(stg, reinterpret_cast<const T*>(a.delta) + b * a.delta_bs + d * a.delta_ds,
-                                      stg + 4 * kSeg, reinterpret_cast<const T*>(a.u) + b * a.u_bs + d * a.u_ds, span, tr, tb);
-            if (a.z) frames_gather2<T, 8, kKP>(stg + 8 * kSeg, reinterpret_cast<const T*>(a.dout) + b * a.dout_bs + dg * a.dout_ds,
-                                               stg + 12 * kSeg, reinterpret_cast<const T*>(a.z) + b * a.z_bs + dg * a.z_ds, span, tr, tb);
-            else frames_gather<T, 8, kKP>(stg + 8 * kSeg, reinterpret_cast<const T*>(a.dout) + b * a.dout_bs + dg * a.dout_ds, span, tr, tb);
+            fg_dt.load(reinterpret_cast<const T*>(a.delta) + b * a.delta_bs + d * a.delta_ds, span, tr, tb);
+            fg_u.load(reinterpret_cast<const T*>(a.u) + b * a.u_bs + d * a.u_ds, span, tr, tb);
+            fg_g.load(reinterpret_cast<const T*>(a.dout) + b * a.dout_bs + dg * a.dout_ds, span, tr, tb);
+            if (a.z) fg_z.load(reinterpret_cast<const T*>(a.z) + b * a.z_bs + dg * a.z_ds, span, tr, tb);
         }
-        __syncwarp();
-        r_dt.load_staged(stg, tb * 8, t0, L);
-        r_u.load_staged(stg + 4 * kSeg, tb * 8, t0, L);
-        r_g.load_staged(stg + 8 * kSeg, tb * 8, t0, L);
-        if (a.z) r_z.load_staged(stg + 12 * kSeg, tb * 8, t0, L);
-        __syncwarp();
     } else {
         r_dt.load_trav(reinterpret_cast<const T*>(a.delta) + b * a.delta_bs + d * a.delta_ds, t0, tr);
         r_u.load_trav(reinterpret_cast<const T*>(a.u) + b * a.u_bs + d * a.u_ds, t0, tr);
@@ -211,6 +204,22 @@ __global__ void __launch_bounds__(kBwdThreads, 4) seg_bwd_kernel(const vv_scan_a
         tE[j] = n2 < N ? a.chk[tck[j]] : 0.f;   // written by the forward pass: no dependency on the predecessor kernel
     }
     pdl_trigger();
+    if (staged) {
+        // staging rows of the warp's 4 channels x 4 tensors: the warp's own dB / dC tile, not used before the state loop
+        T* stg = reinterpret_cast<T*>(tdB) + cg * kSeg;
+        if (live) {
+            fg_dt.store(stg, span, tr, tb);
+            fg_u.store(stg + 4 * kSeg, span, tr, tb);
+            fg_g.store(stg + 8 * kSeg, span, tr, tb);
+            if (a.z) fg_z.store(stg + 12 * kSeg, span, tr, tb);
+        }
+        __syncwarp();
+        r_dt.load_staged(stg, tb * 8, t0, L);
+        r_u.load_staged(stg + 4 * kSeg, tb * 8, t0, L);
+        r_g.load_staged(stg + 8 * kSeg, tb * 8, t0, L);
+        if (a.z) r_z.load_staged(stg + 12 * kSeg, tb * 8, t0, L);
+        __syncwarp();
+    }
 
     // ---- per-position quantities of this lane's channel (fp32 pairs, registers)
     float2 dt2[4], drive2[4], g2[4];

@@ -11,6 +11,7 @@
 #include "conv1d.cuh"
 #include "conv1d_dirs.cuh"
 #include "dwconv3d.cuh"
+#include "layernorm.cuh"
 #include "scan_bwd.cuh"
 #include "scan_seq.cuh"
 
@@ -189,6 +190,73 @@ int launch_conv_dirs(const vv_conv1d_dirs_args* a, void* stream) {
         case VV_F16: return launch_conv_dirs_t<__half, kBwd>(b, vec, pt, st);
         default: return launch_conv_dirs_t<__nv_bfloat16, kBwd>(b, vec, pt, st);
     }
+}
+
+// ---------------------------------------------------------------- LayerNorm dispatch
+template <typename TI, typename TO, int V, bool kBwd>
+int launch_ln_k(const vv_layernorm_args& a, int K, cudaStream_t st) {
+    const int64_t want = (a.rows + vv::kLnWarps - 1) / vv::kLnWarps;
+    // forward: one row per warp and trip; backward: few enough CTAs that the per-CTA channel atomics stay cheap
+    const unsigned grid = (unsigned)std::max<int64_t>(1, std::min<int64_t>(want, (int64_t)sm_count() * (kBwd ? 4 : 16)));
+#define VV_LN_LAUNCH(KK)                                                                                   \
+    do {                                                                                                   \
+        if (kBwd) vv::layernorm_bwd_kernel<TI, TO, V, KK><<<grid, vv::kLnThreads, 0, st>>>(a);             \
+        else vv::layernorm_fwd_kernel<TI, TO, V, KK><<<grid, vv::kLnThreads, 0, st>>>(a);                  \
+    } while (0)
+    if constexpr (V == 4) {
+        switch (K) {
+            case 1: VV_LN_LAUNCH(1); break;
+            case 2: VV_LN_LAUNCH(2); break;
+            case 3: VV_LN_LAUNCH(3); break;
+            default: VV_LN_LAUNCH(4); break;
+        }
+    } else {
+        if (K <= 4) VV_LN_LAUNCH(4);
+        else if (K <= 8) VV_LN_LAUNCH(8);
+        else VV_LN_LAUNCH(16);
+    }
+#undef VV_LN_LAUNCH
+    return check_launch(kBwd ? "layernorm_bwd_kernel" : "layernorm_fwd_kernel");
+}
+
+template <typename TI, typename TO, bool kBwd>
+int launch_ln_t(const vv_layernorm_args& a, cudaStream_t st) {
+    const int ei = sizeof(TI), eo = sizeof(TO);
+    auto ok4 = [](const void* p, int64_t rs, int es) {
+        return p == nullptr || (reinterpret_cast<uintptr_t>(p) % (4 * es) == 0 && (rs * es) % (4 * es) == 0);
+    };
+    bool vec = a.channels % 4 == 0 && ok4(a.x, a.x_rs, ei) && !force_scalar_io();
+    if (kBwd) vec = vec && ok4(a.dout, a.dout_rs, eo) && ok4(a.dx, a.dx_rs, ei);
+    else vec = vec && ok4(a.out, a.out_rs, eo);
+    if (vec) return launch_ln_k<TI, TO, 4, kBwd>(a, (a.channels / 4 + 31) / 32, st);
+    return launch_ln_k<TI, TO, 1, kBwd>(a, (a.channels + 31) / 32, st);
+}
+
+template <bool kBwd>
+int launch_ln(const vv_layernorm_args* a, void* stream) {
+    g_launches = 0;
+    if (!a) return fail(VV_ERR_BAD_ARG, "layernorm: null args");
+    if (!a->x || !a->mean || !a->rstd) return fail(VV_ERR_BAD_ARG, "layernorm: x, mean and rstd are required");
+    if (!kBwd && !a->out) return fail(VV_ERR_BAD_ARG, "layernorm_fwd: out is required");
+    if (kBwd && !a->dout) return fail(VV_ERR_BAD_ARG, "layernorm_bwd: dout is required");
+    if (a->rows <= 0 || a->channels <= 0) return fail(VV_ERR_BAD_ARG, "layernorm: sizes must be positive");
+    if (a->channels > 512) return fail(VV_ERR_UNSUPPORTED, "layernorm: this build serves channels <= 512 (got %d)", a->channels);
+    if (!valid_dtype(a->io_dtype) || !valid_dtype(a->out_dtype)) return fail(VV_ERR_BAD_ARG, "layernorm: dtype must be fp32, fp16 or bf16");
+    if (a->out_dtype != a->io_dtype && a->io_dtype != VV_F32)
+        return fail(VV_ERR_UNSUPPORTED, "layernorm: out_dtype must equal io_dtype unless io_dtype is float32");
+    if (!elem_aligned(a->x, elem_size(a->io_dtype)) || !elem_aligned(a->dx, elem_size(a->io_dtype)) ||
+        !elem_aligned(a->out, elem_size(a->out_dtype)) || !elem_aligned(a->dout, elem_size(a->out_dtype)))
+        return fail(VV_ERR_ALIGN, "layernorm: tensor not aligned to its element size");
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    if (a->io_dtype == VV_F32) {
+        switch (a->out_dtype) {
+            case VV_F32: return launch_ln_t<float, float, kBwd>(*a, st);
+            case VV_F16: return launch_ln_t<float, __half, kBwd>(*a, st);
+            default: return launch_ln_t<float, __nv_bfloat16, kBwd>(*a, st);
+        }
+    }
+    if (a->io_dtype == VV_F16) return launch_ln_t<__half, __half, kBwd>(*a, st);
+    return launch_ln_t<__nv_bfloat16, __nv_bfloat16, kBwd>(*a, st);
 }
 
 // ---------------------------------------------------------------- depthwise conv3d dispatch
@@ -535,6 +603,8 @@ int vv_conv1d_dirs_fwd(const vv_conv1d_dirs_args* a, void* stream) { return laun
 int vv_conv1d_dirs_bwd(const vv_conv1d_dirs_args* a, void* stream) { return launch_conv_dirs<true>(a, stream); }
 int vv_dwconv3d_fwd(const vv_dwconv3d_args* a, void* stream) { return launch_dw<false>(a, stream); }
 int vv_dwconv3d_bwd(const vv_dwconv3d_args* a, void* stream) { return launch_dw<true>(a, stream); }
+int vv_layernorm_fwd(const vv_layernorm_args* a, void* stream) { return launch_ln<false>(a, stream); }
+int vv_layernorm_bwd(const vv_layernorm_args* a, void* stream) { return launch_ln<true>(a, stream); }
 int vv_scan_fwd(const vv_scan_args* a, void* stream) { return launch_scan<false>(a, stream); }
 int vv_scan_bwd(const vv_scan_args* a, void* stream) { return launch_scan<true>(a, stream); }
 

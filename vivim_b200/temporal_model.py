@@ -28,6 +28,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
+from .layernorm import TokenLayerNorm
 from .mamba_simple import Mamba
 
 B3 = dict(num_channels=3, num_encoder_blocks=4, depths=[3, 4, 18, 3], sr_ratios=[8, 4, 2, 1],
@@ -97,9 +98,11 @@ class TemporalMambaBlock(nn.Module):
 
     def __init__(self, dim, drop_path=0.0, mlp_ratio=4):
         super().__init__()
-        self.norm1 = nn.LayerNorm(dim)
+        # nn.LayerNorm parameters on the sm_100a kernels; under autocast they hand bf16 straight to the GEMMs that follow
+        self.norm1 = TokenLayerNorm(dim)
         self.mamba = Mamba(d_model=dim, d_state=16, d_conv=4, expand=2, bimamba_type="v3")
-        self.norm2 = nn.LayerNorm(dim)
+        self.norm2 = TokenLayerNorm(dim)
+        self.norm1.autocast_output = self.norm2.autocast_output = True
         self.mlp = _TokenMlp(dim, int(dim * mlp_ratio))
         self.drop_path_rate = float(drop_path)
         self.apply(_reference_init)
