@@ -373,6 +373,21 @@ def graphs_for(sets, lib, device, torch):
     return graphs
 
 
+def teardown(dist, world):
+    """Leave the process group without ever hanging the job: the result line is already printed and flushed."""
+    if world <= 1:
+        return
+    import threading as _th
+    _th.Timer(30.0, lambda: os._exit(0)).start()     # a communicator teardown that blocks must not keep the launcher alive
+    try:
+        import torch
+        torch.cuda.synchronize()
+        dist.barrier()
+        dist.destroy_process_group()
+    finally:
+        os._exit(0)
+
+
 def run_ours(args, rank, world, local_rank):
     import torch
     import torch.distributed as dist
@@ -496,8 +511,7 @@ def run_ours(args, rank, world, local_rank):
         launches += vivim.pop("_launches", 0)
 
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
+        teardown(dist, world)
         return
     # Second roofline, the one that actually binds these kernels: MUFU.EX2 lane-operations per pass (one per state-step
     # for the decay, plus softplus / sigmoid in the per-position pre-pass) against the measured MUFU rate
@@ -537,8 +551,8 @@ def run_ours(args, rank, world, local_rank):
         line["cpu_baseline"] = cpu_baseline_obj(cpu_v, cores, clips, ndirs,
                                                 None if args.quick else {"torch_port_selective_scan_ref": time_torch_port()})
     print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+    sys.stdout.flush()
+    teardown(dist, world)
 
 
 def bench_conv(clips, ndirs, device, torch):
@@ -777,6 +791,7 @@ def bench_vivim(args, rank, world, device, torch, dist):
                                                "one NCCL all_reduce(AVG) of the flat fp32 gradient (%.0f MB) after the graph replay"
                                                % (tsg.flat_grad.numel() * 4 / 1e6)),
                             "launch": "forward + backward as one CUDA graph (vivim_b200.graphed.TrainStepGraph)"})
+    tsg.close()         # the graph holds NCCL nodes: release it before the process group is torn down
     del tsg, opt
     # ---- inference (configs[3]: 32 clips over 8 GPUs -> 4 per GPU)
     batch = 4
@@ -791,7 +806,10 @@ def bench_vivim(args, rank, world, device, torch, dist):
                                          "nn.LayerNorm modules" % n_ln) if n_ln else "vivim_b200 TokenLayerNorm in the Temporal Mamba blocks only",
                            "model": "vivim_b200.temporal_model.Vivim (restates modeling/vivim.py; state-dict compatible)"}
     res["_launches"] = launches
+    infer.graph.reset()
     del infer, model
+    import gc
+    gc.collect()
     torch.cuda.empty_cache()
     return res
 

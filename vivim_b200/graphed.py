@@ -104,8 +104,8 @@ class TrainStepGraph:
             if off > lo:
                 self._buckets.append((lo, off))
             self._bucket_params = [owner.count(b) for b in range(len(self._buckets))]
-            for p, b in zip(self.params, owner):
-                p.register_post_accumulate_grad_hook(lambda _p, b=b: self._grad_ready(b))
+            self._hooks = [p.register_post_accumulate_grad_hook(lambda _p, b=b: self._grad_ready(b))
+                           for p, b in zip(self.params, owner)]
         side = torch.cuda.Stream(device)
         side.wait_stream(torch.cuda.current_stream(device))
         with torch.cuda.stream(side):
@@ -150,6 +150,18 @@ class TrainStepGraph:
                     self._reduce_bucket(b)
             torch.cuda.current_stream().wait_stream(self.comm_stream)    # join
         self.loss.copy_(loss.detach())
+
+    def close(self):
+        """Release the captured graph (and the gradient hooks).  Call this before ``dist.destroy_process_group()`` when
+        the graph contains collectives: a live CUDA graph keeps its NCCL nodes alive and the communicator teardown waits
+        on them."""
+        for h in getattr(self, "_hooks", []):
+            h.remove()
+        self._hooks = []
+        torch.cuda.synchronize()
+        if getattr(self, "graph", None) is not None:
+            self.graph.reset()
+            self.graph = None
 
     def __call__(self, *batch):
         """Copy ``batch`` (inputs followed by targets; omit to reuse the captured tensors) into the static buffers and
