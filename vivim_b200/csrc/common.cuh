@@ -412,6 +412,36 @@ __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefe
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
+// ---------------------------------------------------------------- TMA (cp.async.bulk.tensor) + mbarrier
+// One elected thread arms an mbarrier with the byte count of the tile and issues the bulk tensor copy; the copy engine
+// writes the box into shared memory and completes the barrier; every thread then waits on its phase.
+__device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");   // make the init visible to the async proxy
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, unsigned parity) {
+    unsigned ok;
+    asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+                 : "=r"(ok) : "r"((unsigned)__cvta_generic_to_shared(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
+// bounded wait: a copy that never lands must trap, not hang the GPU
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
+    for (int it = 0; it < (1 << 24); ++it)
+        if (mbar_try_wait(bar, parity)) return;
+    __trap();
+}
+// 2-D box at (x = position, y = row) of the tensor described by `tmap` -> shared `dst` (128-byte aligned)
+__device__ __forceinline__ void tma_load_2d(void* dst, const void* tmap, int x, int y, uint64_t* bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 ::"r"((unsigned)__cvta_generic_to_shared(dst)), "l"(tmap), "r"((unsigned)__cvta_generic_to_shared(bar)), "r"(x), "r"(y)
+                 : "memory");
+}
+
 // packed fp32 pairs (FFMA2 / FMUL2 / FADD2 of sm_100): one issue slot for two lanes of fp32 math
 __device__ __forceinline__ float2 mul2(float2 x, float2 y) { return __fmul2_rn(x, y); }
 __device__ __forceinline__ float2 add2(float2 x, float2 y) { return __fadd2_rn(x, y); }

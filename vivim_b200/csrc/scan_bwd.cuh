@@ -133,9 +133,19 @@ struct BwdTileLoader {
 //   du = D g + dt sum_n r B            ddt = u sum_n r B + sum_n A_n w
 //   dA_n = sum_t dt w                  dB_n = sum_d r dt u          dC_n = sum_d g h
 // NB: compile-time state block (8, 16, 32) >= N; rows N..NB-1 are zero padding.
-template <typename T, bool kVec, int NB, bool kGen>
-__global__ void __launch_bounds__(kBwdThreads, 4) seg_bwd_kernel(const vv_scan_args a) {
-    extern __shared__ float4 smem4[];
+// Tensor maps of B and C for the TMA variant of the tile fill (kTma): rank 2, dims (L, B*G*N), box (64, N).
+struct BwdTmaMaps {
+    alignas(64) unsigned char B[128];
+    alignas(64) unsigned char C[128];
+};
+
+// kTma (measurement variant, VV_TMA_BC=1; plain launches, 16-bit I/O): the B / C tiles of the segment arrive by
+// cp.async.bulk.tensor into a raw 16-bit staging area (aliasing warp 0's dB / dC tile) instead of through registers, and
+// are then expanded into the fp32 [state][position] tiles.  Measured against the register route in profiles/r02_tma.md.
+template <typename T, bool kVec, int NB, bool kGen, bool kTma = false>
+__global__ void __launch_bounds__(kBwdThreads, 4) seg_bwd_kernel(const vv_scan_args a, const __grid_constant__ BwdTmaMaps maps) {
+    extern __shared__ __align__(128) float4 smem4[];
+    __shared__ __align__(8) uint64_t tma_bar;
     const int L = a.seqlen, N = a.dstate;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int cg = lane >> 3, tb = lane & 7;
@@ -184,8 +194,20 @@ __global__ void __launch_bounds__(kBwdThreads, 4) seg_bwd_kernel(const vv_scan_a
         if (a.z) r_z.load_trav(reinterpret_cast<const T*>(a.z) + b * a.z_bs + dg * a.z_ds, t0, tr);
     }
     BwdTileLoader<T, kVec, NB> lB, lC;
-    lB.load(reinterpret_cast<const T*>(a.Bm) + b * a.B_bs + grp * a.B_gs, a.B_ns, a.B_ls, N, t0s, tr, kGen);
-    lC.load(reinterpret_cast<const T*>(a.Cm) + b * a.C_bs + grp * a.C_gs, a.C_ns, a.C_ls, N, t0s, tr, kGen);
+    T* tma_stage = reinterpret_cast<T*>(tC + NB * kBwdSlots);      // warp 0's dB / dC tile: free until the state loop
+    if (kTma) {
+        if (threadIdx.x == 0) mbar_init(&tma_bar, 1);
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            const int row0 = (b * a.ngroups + grp) * N;             // first state row of this (batch, group) in (B*G*N, L)
+            mbar_expect_tx(&tma_bar, 2u * (unsigned)(N * kSeg * sizeof(T)));
+            tma_load_2d(tma_stage, maps.B, t0s, row0, &tma_bar);
+            tma_load_2d(tma_stage + N * kSeg, maps.C, t0s, row0, &tma_bar);
+        }
+    } else {
+        lB.load(reinterpret_cast<const T*>(a.Bm) + b * a.B_bs + grp * a.B_gs, a.B_ns, a.B_ls, N, t0s, tr, kGen);
+        lC.load(reinterpret_cast<const T*>(a.Cm) + b * a.C_bs + grp * a.C_gs, a.C_ns, a.C_ls, N, t0s, tr, kGen);
+    }
     const float bias = a.delta_bias ? a.delta_bias[d] : 0.f;
     const float Dv = a.D ? a.D[d] : 0.f;
     const bool sp = a.delta_softplus != 0;
@@ -254,8 +276,33 @@ __global__ void __launch_bounds__(kBwdThreads, 4) seg_bwd_kernel(const vv_scan_a
             g2[jp] = make_float2(g[2 * jp], g[2 * jp + 1]);
         }
     }
-    lB.store(tB);
-    lC.store(tC);
+    if (kTma) {
+        // the boxes have landed as [state][64 positions] in the I/O dtype (positions >= L zero-filled by the copy engine):
+        // expand them into the fp32 tiles, thread = (state, 8 positions)
+        mbar_wait(&tma_bar, 0);
+#pragma unroll
+        for (int j = 0; j < (NB * 8 + kBwdThreads - 1) / kBwdThreads; ++j) {
+            const int idx = threadIdx.x + j * kBwdThreads;
+            const int n = idx >> 3, c8 = idx & 7;
+            if (n < NB) {
+                float vb[8], vc[8];
+                if (n < N) {
+                    load8_plain<T>(tma_stage + n * kSeg + c8 * 8, vb);
+                    load8_plain<T>(tma_stage + (N + n) * kSeg + c8 * 8, vc);
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) vb[i] = vc[i] = 0.f;
+                }
+                tB[n * kBwdSlots + c8] = make_float4(vb[0], vb[1], vb[2], vb[3]);
+                tB[n * kBwdSlots + 8 + c8] = make_float4(vb[4], vb[5], vb[6], vb[7]);
+                tC[n * kBwdSlots + c8] = make_float4(vc[0], vc[1], vc[2], vc[3]);
+                tC[n * kBwdSlots + 8 + c8] = make_float4(vc[4], vc[5], vc[6], vc[7]);
+            }
+        }
+    } else {
+        lB.store(tB);
+        lC.store(tC);
+    }
     pdl_wait();   // chk is from the forward pass, radj from the reverse carry kernel just before us
 #pragma unroll
     for (int j = 0; j < kTab; ++j) {

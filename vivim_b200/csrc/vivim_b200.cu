@@ -1,11 +1,13 @@
 // vivim_b200.cu -- C ABI (include/vivim_b200.h) and launch logic for the sm_100a kernels.
 // Argument checks mirror the reference shims' TORCH_CHECKs
 // (causal-conv1d/csrc/causal_conv1d.cpp:130-268, mamba/csrc/selective_scan/selective_scan.cpp:226-492).
+#include <cuda.h>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <algorithm>
+#include <type_traits>
 
 #include "../../include/vivim_b200.h"
 #include "conv1d.cuh"
@@ -500,6 +502,51 @@ int launch_seg_carry(const vv_scan_args& a, const SegPlan& p, cudaStream_t st) {
         default: { constexpr int NB = 32; __VA_ARGS__; break; } \
     }
 
+// ---- TMA variant of the backward's B / C tile fill (measurement: VV_TMA_BC=1, see profiles/r02_tma.md)
+bool tma_bc_enabled() {
+    static const bool on = env_int("VV_TMA_BC", 0) != 0;
+    return on;
+}
+
+// rank-2 tensor maps over B and C viewed as (B*G*N rows, L) with a (64 positions x N rows) box; false = not encodable
+// (layout not contiguous in (N, L), strides not multiples of 16 bytes, driver entry point missing): the caller then
+// takes the register route.
+template <typename T>
+bool encode_bc_maps(const vv_scan_args& a, vv::BwdTmaMaps& maps) {
+    typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                 const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                 CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static EncodeFn encode = [] {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) != cudaSuccess ||
+            q != cudaDriverEntryPointSuccess)
+            fn = nullptr;
+        return reinterpret_cast<EncodeFn>(fn);
+    }();
+    if (!encode) return false;
+    const int64_t N = a.dstate, L = a.seqlen, G = a.ngroups;
+    auto contiguous = [&](int64_t bs, int64_t gs, int64_t ns) { return ns == L && gs == N * L && bs == G * N * L; };
+    if (!contiguous(a.B_bs, a.B_gs, a.B_ns) || !contiguous(a.C_bs, a.C_gs, a.C_ns) || (L * (int64_t)sizeof(T)) % 16 != 0) return false;
+    static_assert(sizeof(CUtensorMap) <= 128, "CUtensorMap does not fit the kernel parameter slot");
+    const cuuint64_t dims[2] = {(cuuint64_t)L, (cuuint64_t)(a.batch * G * N)};
+    const cuuint64_t strides[1] = {(cuuint64_t)(L * sizeof(T))};
+    const cuuint32_t box[2] = {(cuuint32_t)vv::kSeg, (cuuint32_t)N};
+    const cuuint32_t estr[2] = {1, 1};
+    const CUtensorMapDataType dt = std::is_same<T, __half>::value ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+    const void* ptrs[2] = {a.Bm, a.Cm};
+    unsigned char* dst[2] = {maps.B, maps.C};
+    for (int i = 0; i < 2; ++i) {
+        if (reinterpret_cast<uintptr_t>(ptrs[i]) % 16 != 0) return false;
+        CUtensorMap m;
+        if (encode(&m, dt, 2, const_cast<void*>(ptrs[i]), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+            return false;
+        memcpy(dst[i], &m, sizeof(m));
+    }
+    return true;
+}
+
 template <typename T, bool kVec>
 int scan_fwd_t(const vv_scan_args& a, cudaStream_t st) {
     const SegPlan p = plan_seg(a);
@@ -534,9 +581,13 @@ int scan_bwd_t(const vv_scan_args& a, cudaStream_t st) {
         const dim3 grid(sp.segs, a.ngroups * ((dpg + vv::kBwdRows - 1) / vv::kBwdRows), a.batch);
         VV_NB_SWITCH(sp.NB, {
             const size_t smem = vv::bwd_smem_bytes(NB);
-            auto kernel = plain_scan(a) ? vv::seg_bwd_kernel<T, kVec, NB, false> : vv::seg_bwd_kernel<T, kVec, NB, true>;
+            vv::BwdTmaMaps maps;
+            memset(&maps, 0, sizeof(maps));
+            const bool tma = kVec && sizeof(T) == 2 && plain_scan(a) && tma_bc_enabled() && encode_bc_maps<T>(a, maps);
+            auto kernel = tma ? vv::seg_bwd_kernel<T, kVec && sizeof(T) == 2, NB, false, kVec && sizeof(T) == 2>
+                        : plain_scan(a) ? vv::seg_bwd_kernel<T, kVec, NB, false, false> : vv::seg_bwd_kernel<T, kVec, NB, true, false>;
             if ((rc = set_smem(kernel, smem)) != VV_OK) return rc;
-            launch_kernel(kernel, grid, dim3(vv::kBwdThreads), smem, st, use_pdl() && (pass_mask(a) & 2), a);
+            launch_kernel(kernel, grid, dim3(vv::kBwdThreads), smem, st, use_pdl() && (pass_mask(a) & 2), a, maps);
         });
         if ((rc = check_launch("seg_bwd_kernel")) != VV_OK) return rc;
     }

@@ -45,6 +45,23 @@ def graph_module(module: nn.Module, sample_args, autocast_dtype=None, num_warmup
     return torch.cuda.make_graphed_callables(target, tuple(sample_args), num_warmup_iters=num_warmup_iters)
 
 
+def bucket_ranges(numels, limit):
+    """Cut a flat buffer holding tensors of ``numels`` elements (in order) into contiguous buckets of at least ``limit``
+    elements (the last one may be smaller), never splitting a tensor.  Returns (list of (lo, hi) element ranges, bucket
+    index of every tensor)."""
+    buckets, owner = [], []
+    lo = off = 0
+    for n in numels:
+        owner.append(len(buckets))
+        off += n
+        if off - lo >= limit:
+            buckets.append((lo, off))
+            lo = off
+    if off > lo:
+        buckets.append((lo, off))
+    return buckets, owner
+
+
 class TrainStepGraph:
     """Forward + backward of a whole network as ONE CUDA graph, for fixed-shape training steps.
 
@@ -92,17 +109,7 @@ class TrainStepGraph:
         self._buckets, self._in_step = [], False
         if grad_allreduce is not None:
             self.comm_stream = torch.cuda.Stream(device)
-            limit = int(bucket_mb * 1e6 / 4)
-            lo = off = 0
-            owner = []
-            for p in self.params:
-                owner.append(len(self._buckets))
-                off += p.numel()
-                if off - lo >= limit:
-                    self._buckets.append((lo, off))
-                    lo = off
-            if off > lo:
-                self._buckets.append((lo, off))
+            self._buckets, owner = bucket_ranges([p.numel() for p in self.params], int(bucket_mb * 1e6 / 4))
             self._bucket_params = [owner.count(b) for b in range(len(self._buckets))]
             self._hooks = [p.register_post_accumulate_grad_hook(lambda _p, b=b: self._grad_ready(b))
                            for p, b in zip(self.params, owner)]
