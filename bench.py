@@ -403,6 +403,13 @@ def run_ours(args, rank, world, local_rank):
         os.environ.setdefault("TORCH_NCCL_ASYNC_ERROR_HANDLING", "0")
         dist.init_process_group("nccl", device_id=device)
 
+    if args.only_vivim:      # development: the whole-network legs alone (not a bench line)
+        v = bench_vivim(args, rank, world, device, torch, dist)
+        v.pop("_launches", None)
+        if rank == 0:
+            print(json.dumps({"n_gpus": world, **v}), flush=True)
+        teardown(dist, world)
+        return
     clips, ndirs = args.clips, args.dirs
     fwd_b, bwd_b = algo_bytes(clips * ndirs)
     cfg, n_sets = workload_config(clips, ndirs)
@@ -827,6 +834,7 @@ def main():
     ap.add_argument("--dir-modes", default=None, help="kernel development: comma list overriding the traversal order of the "
                                                       "direction blocks, e.g. fwd,fwd,fwd")
     ap.add_argument("--no-vivim", action="store_true", help="skip the whole-network clips/s legs")
+    ap.add_argument("--only-vivim", action="store_true", help="development: run only the whole-network legs")
     ap.add_argument("--torch-layernorm", action="store_true", help="keep torch's LayerNorm in the SegFormer stages")
     ap.add_argument("--no-overlap", action="store_true", help="training: one all-reduce after the graph replay instead of "
                                                               "bucketed all-reduces captured inside the graph")

@@ -8,6 +8,9 @@ for path in sys.argv[1:]:
         if not line.startswith("{"):
             continue
         d = json.loads(line)
+        if "metric" not in d:
+            print(f"== {path}: n_gpus {d.get('n_gpus')}  " + "  ".join(f"{k} {d[k]:.2f}" for k in d if k.endswith(("_per_s", "_per_step"))))
+            continue
         print(f"== {path}: {d.get('config', {}).get('directions')} value {d.get('value', 0):.1f} GB/s  step {d.get('ms_per_step', 0) * 1e3:.1f} us"
               f"  per-scan {d.get('us_per_direction_scan', 0):.1f} us  e2e {d.get('e2e', {}).get('value', 0):.1f}")
         if "kernel_us" in d:
