@@ -211,39 +211,55 @@ constexpr int kFramesMaxNf = 8;
 template <int NL, int KP>
 __host__ __device__ constexpr bool frames_fits(int nf, int len) { return nf >= 2 && nf <= kFramesMaxNf && (len / nf + 2) <= NL * KP; }
 
-template <typename T, int NL, int KP, int NF>
-struct FramesGather {
-    T v[NF][KP];
-    __device__ __forceinline__ void load(const T* __restrict__ row, const FramesSpan& s, const Trav& tr, int sub) {
+// Per-frame bookkeeping of one lane, shared by every tensor it gathers / scatters: first pixel, number of further pixels
+// (cnt < 0: none), element offset in the global row and in the traversal-ordered shared row.  Per element that leaves one
+// compare and constant offsets from two per-frame base pointers.
+template <int NL, int NF>
+struct FramesLanePlan {
+    int cnt[NF], goff[NF], soff[NF];
+    __device__ __forceinline__ FramesLanePlan(const FramesSpan& s, const Trav& tr, int sub) {
 #pragma unroll
         for (int t = 0; t < NF; ++t) {
             const int plo = s.p_first + (t < s.t_first ? 1 : 0), phi = s.p_last - (t > s.t_last ? 1 : 0);
-#pragma unroll
-            for (int k = 0; k < KP; ++k) {
-                const int p = plo + sub + k * NL;
-                if (t < tr.nf && p <= phi && s.j0 < tr.L) v[t][k] = row[(int64_t)t * tr.hw + p];
-            }
-        }
-    }
-    __device__ __forceinline__ void store(T* __restrict__ dst, const FramesSpan& s, const Trav& tr, int sub) const {
-#pragma unroll
-        for (int t = 0; t < NF; ++t) {
-            const int plo = s.p_first + (t < s.t_first ? 1 : 0), phi = s.p_last - (t > s.t_last ? 1 : 0);
-#pragma unroll
-            for (int k = 0; k < KP; ++k) {
-                const int p = plo + sub + k * NL;
-                if (t < tr.nf && p <= phi && s.j0 < tr.L) dst[p * tr.nf + t - s.j0] = v[t][k];
-            }
+            const int p = plo + sub;
+            cnt[t] = (t < tr.nf && s.j0 < tr.L) ? phi - p : -1;
+            goff[t] = t * tr.hw + p;
+            soff[t] = p * tr.nf + t - s.j0;
         }
     }
 };
+
+template <typename T, int NL, int KP, int NF>
+struct FramesGather {
+    T v[NF][KP];
+    __device__ __forceinline__ void load(const T* __restrict__ row, const FramesLanePlan<NL, NF>& pl) {
+#pragma unroll
+        for (int t = 0; t < NF; ++t) {
+            const T* src = row + pl.goff[t];
+#pragma unroll
+            for (int k = 0; k < KP; ++k)
+                if (k * NL <= pl.cnt[t]) v[t][k] = src[k * NL];
+        }
+    }
+    __device__ __forceinline__ void store(T* __restrict__ dst, const FramesLanePlan<NL, NF>& pl, int nf) const {
+#pragma unroll
+        for (int t = 0; t < NF; ++t) {
+            T* d = dst + pl.soff[t];
+#pragma unroll
+            for (int k = 0; k < KP; ++k)
+                if (k * NL <= pl.cnt[t]) d[k * NL * nf] = v[t][k];
+        }
+    }
+};
+
 // NF: static bound on nframes (5 covers Vivim's clips with 3/8 fewer registers in flight than kFramesMaxNf)
 template <typename T, int NL, int KP, int NF>
 __device__ __forceinline__ void frames_gather_n(T* __restrict__ dst, const T* __restrict__ row, const FramesSpan& s,
                                                 const Trav& tr, int sub) {
+    const FramesLanePlan<NL, NF> pl(s, tr, sub);
     FramesGather<T, NL, KP, NF> g;
-    g.load(row, s, tr, sub);
-    g.store(dst, s, tr, sub);
+    g.load(row, pl);
+    g.store(dst, pl, tr.nf);
 }
 template <typename T, int NL, int KP>
 __device__ __forceinline__ void frames_gather(T* __restrict__ dst, const T* __restrict__ row, const FramesSpan& s,
@@ -251,34 +267,29 @@ __device__ __forceinline__ void frames_gather(T* __restrict__ dst, const T* __re
     if (tr.nf <= 5) frames_gather_n<T, NL, KP, 5>(dst, row, s, tr, sub);
     else frames_gather_n<T, NL, KP, kFramesMaxNf>(dst, row, s, tr, sub);
 }
-// two rows at once: both rows' loads in flight together
-template <typename T, int NL, int KP, int NF>
-__device__ __forceinline__ void frames_gather2_n(T* __restrict__ dst0, const T* __restrict__ row0, T* __restrict__ dst1,
-                                                 const T* __restrict__ row1, const FramesSpan& s, const Trav& tr, int sub) {
-    FramesGather<T, NL, KP, NF> g0, g1;
-    g0.load(row0, s, tr, sub);
-    g1.load(row1, s, tr, sub);
-    g0.store(dst0, s, tr, sub);
-    g1.store(dst1, s, tr, sub);
-}
-template <typename T, int NL, int KP>
-__device__ __forceinline__ void frames_gather2(T* __restrict__ dst0, const T* __restrict__ row0, T* __restrict__ dst1,
-                                               const T* __restrict__ row1, const FramesSpan& s, const Trav& tr, int sub) {
-    if (tr.nf <= 5) frames_gather2_n<T, NL, KP, 5>(dst0, row0, dst1, row1, s, tr, sub);
-    else frames_gather2_n<T, NL, KP, kFramesMaxNf>(dst0, row0, dst1, row1, s, tr, sub);
-}
+
 // shared row src[0..len) (traversal order) -> global row (memory order)
+template <typename T, int NL, int KP, int NF>
+__device__ __forceinline__ void frames_scatter_n(T* __restrict__ row, const T* __restrict__ src, const FramesLanePlan<NL, NF>& pl,
+                                                 int nf) {
+#pragma unroll
+    for (int t = 0; t < NF; ++t) {
+        T* d = row + pl.goff[t];
+        const T* sp = src + pl.soff[t];
+#pragma unroll
+        for (int k = 0; k < KP; ++k)
+            if (k * NL <= pl.cnt[t]) d[k * NL] = sp[k * NL * nf];
+    }
+}
 template <typename T, int NL, int KP>
 __device__ __forceinline__ void frames_scatter(T* __restrict__ row, const T* __restrict__ src, const FramesSpan& s,
                                                const Trav& tr, int sub) {
-#pragma unroll
-    for (int t = 0; t < kFramesMaxNf; ++t) {
-        const int plo = s.p_first + (t < s.t_first ? 1 : 0), phi = s.p_last - (t > s.t_last ? 1 : 0);
-#pragma unroll
-        for (int k = 0; k < KP; ++k) {
-            const int p = plo + sub + k * NL;
-            if (t < tr.nf && p <= phi && s.j0 < tr.L) row[(int64_t)t * tr.hw + p] = src[p * tr.nf + t - s.j0];
-        }
+    if (tr.nf <= 5) {
+        const FramesLanePlan<NL, 5> pl(s, tr, sub);
+        frames_scatter_n<T, NL, KP, 5>(row, src, pl, tr.nf);
+    } else {
+        const FramesLanePlan<NL, kFramesMaxNf> pl(s, tr, sub);
+        frames_scatter_n<T, NL, KP, kFramesMaxNf>(row, src, pl, tr.nf);
     }
 }
 

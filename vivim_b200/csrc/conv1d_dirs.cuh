@@ -374,10 +374,15 @@ __global__ void __launch_bounds__(kDirsThreads) conv1d_dirs_bwd_kernel(const vv_
                 }
             }
         }
-        for (int t = 0; t < g.nf; ++t) {
-            // element-wise route: everything (kVec = false) or just the 3 positions on either side of the body
-            const int nq = kVec ? 2 * (kDirsHalo - 1) : span;
-            for (int qq = threadIdx.x; qq < nq; qq += kDirsThreads) {
+        // element-wise route: everything (kVec = false) or just the 3 positions on either side of the body.  The items
+        // (frame, position) are dealt to threads 4 apart, so that the few halo items of the 128-bit route are one pass
+        // for every warp instead of nf x 6 passes for warp 0 while the others wait at the barrier.
+        const int nq = kVec ? 2 * (kDirsHalo - 1) : span;
+        const int items = g.nf * nq;
+        const int first = kVec ? ((threadIdx.x & 3) == 0 ? (int)(threadIdx.x >> 2) : items) : (int)threadIdx.x;
+        for (int it = first; it < items; it += kVec ? kDirsThreads / 4 : kDirsThreads) {
+            {
+                const int t = it / nq, qq = it - t * nq;
                 const int q = kVec ? (qq < kDirsHalo - 1 ? qq - (kDirsHalo - 1) : qv + qq - (kDirsHalo - 1))
                                    : qq - (kDirsHalo - 1);
                 const int p = g.p0 + q, m = t * g.hw + p;

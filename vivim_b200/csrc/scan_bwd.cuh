@@ -182,10 +182,11 @@ __global__ void __launch_bounds__(kBwdThreads, 4) seg_bwd_kernel(const vv_scan_a
     FramesGather<T, 8, kKP, kNF> fg_dt, fg_u, fg_g, fg_z;
     if (staged) {
         if (live) {
-            fg_dt.load(reinterpret_cast<const T*>(a.delta) + b * a.delta_bs + d * a.delta_ds, span, tr, tb);
-            fg_u.load(reinterpret_cast<const T*>(a.u) + b * a.u_bs + d * a.u_ds, span, tr, tb);
-            fg_g.load(reinterpret_cast<const T*>(a.dout) + b * a.dout_bs + dg * a.dout_ds, span, tr, tb);
-            if (a.z) fg_z.load(reinterpret_cast<const T*>(a.z) + b * a.z_bs + dg * a.z_ds, span, tr, tb);
+            const FramesLanePlan<8, kNF> pl(span, tr, tb);
+            fg_dt.load(reinterpret_cast<const T*>(a.delta) + b * a.delta_bs + d * a.delta_ds, pl);
+            fg_u.load(reinterpret_cast<const T*>(a.u) + b * a.u_bs + d * a.u_ds, pl);
+            fg_g.load(reinterpret_cast<const T*>(a.dout) + b * a.dout_bs + dg * a.dout_ds, pl);
+            if (a.z) fg_z.load(reinterpret_cast<const T*>(a.z) + b * a.z_bs + dg * a.z_ds, pl);
         }
     } else {
         r_dt.load_trav(reinterpret_cast<const T*>(a.delta) + b * a.delta_bs + d * a.delta_ds, t0, tr);
@@ -230,10 +231,11 @@ __global__ void __launch_bounds__(kBwdThreads, 4) seg_bwd_kernel(const vv_scan_a
         // staging rows of the warp's 4 channels x 4 tensors: the warp's own dB / dC tile, not used before the state loop
         T* stg = reinterpret_cast<T*>(tdB) + cg * kSeg;
         if (live) {
-            fg_dt.store(stg, span, tr, tb);
-            fg_u.store(stg + 4 * kSeg, span, tr, tb);
-            fg_g.store(stg + 8 * kSeg, span, tr, tb);
-            if (a.z) fg_z.store(stg + 12 * kSeg, span, tr, tb);
+            const FramesLanePlan<8, kNF> pl(span, tr, tb);
+            fg_dt.store(stg, pl, tr.nf);
+            fg_u.store(stg + 4 * kSeg, pl, tr.nf);
+            fg_g.store(stg + 8 * kSeg, pl, tr.nf);
+            if (a.z) fg_z.store(stg + 12 * kSeg, pl, tr.nf);
         }
         __syncwarp();
         r_dt.load_staged(stg, tb * 8, t0, L);
@@ -481,6 +483,7 @@ __global__ void __launch_bounds__(kBwdThreads, 4) seg_bwd_kernel(const vv_scan_a
         if (staged && 4 * (int)sizeof(T) <= NB) {
             // FRAMES order: one tensor at a time through a 4-row staging area (the warp's state tables, done with)
             T* ostg = reinterpret_cast<T*>(tabER) + cg * kSeg;
+            const FramesLanePlan<8, kNF> pl(span, tr, tb);
 #pragma unroll
             for (int which = 0; which < 3; ++which) {
                 if (which == 2 && !a.z) break;
@@ -490,7 +493,7 @@ __global__ void __launch_bounds__(kBwdThreads, 4) seg_bwd_kernel(const vv_scan_a
                 T* grow = which == 0 ? reinterpret_cast<T*>(a.du) + b * a.du_bs + d * a.du_ds
                         : which == 1 ? reinterpret_cast<T*>(a.ddelta) + b * a.ddelta_bs + d * a.ddelta_ds
                                      : reinterpret_cast<T*>(a.dz) + b * a.dz_bs + d * a.dz_ds;
-                if (live) frames_scatter<T, 8, kKP>(grow, ostg, span, tr, tb);
+                if (live) frames_scatter_n<T, 8, kKP, kNF>(grow, ostg, pl, tr.nf);
             }
         } else if (live) {
             store8_trav<T, kVec>(reinterpret_cast<T*>(a.du) + b * a.du_bs + d * a.du_ds, t0, tr, du_o);
