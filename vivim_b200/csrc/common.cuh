@@ -467,6 +467,27 @@ template <> __device__ __forceinline__ float2 unpack_pair<float>(uint32_t w) { r
 template <> __device__ __forceinline__ float2 unpack_pair<__half>(uint32_t w) {
     return __half22float2(*reinterpret_cast<const __half2*>(&w));
 }
+// fp32 pair -> two packed 16-bit elements, and the packed add (HADD2 / HADD2.BF16: one issue slot for two sums)
+template <typename T> __device__ __forceinline__ uint32_t pack_pair(float2 v);
+template <> __device__ __forceinline__ uint32_t pack_pair<__nv_bfloat16>(float2 v) {
+    const __nv_bfloat162 h = __floats2bfloat162_rn(v.x, v.y);
+    return *reinterpret_cast<const uint32_t*>(&h);
+}
+template <> __device__ __forceinline__ uint32_t pack_pair<__half>(float2 v) {
+    const __half2 h = __floats2half2_rn(v.x, v.y);
+    return *reinterpret_cast<const uint32_t*>(&h);
+}
+template <> __device__ __forceinline__ uint32_t pack_pair<float>(float2 v) { return __float_as_uint(v.x); }   // never used
+template <typename T> __device__ __forceinline__ uint32_t add_pairs(uint32_t a, uint32_t b);
+template <> __device__ __forceinline__ uint32_t add_pairs<__nv_bfloat16>(uint32_t a, uint32_t b) {
+    const __nv_bfloat162 r = __hadd2(*reinterpret_cast<const __nv_bfloat162*>(&a), *reinterpret_cast<const __nv_bfloat162*>(&b));
+    return *reinterpret_cast<const uint32_t*>(&r);
+}
+template <> __device__ __forceinline__ uint32_t add_pairs<__half>(uint32_t a, uint32_t b) {
+    const __half2 r = __hadd2(*reinterpret_cast<const __half2*>(&a), *reinterpret_cast<const __half2*>(&b));
+    return *reinterpret_cast<const uint32_t*>(&r);
+}
+template <> __device__ __forceinline__ uint32_t add_pairs<float>(uint32_t a, uint32_t) { return a; }   // never used
 // a pair of adjacent elements (4-byte aligned for 16-bit T, 8-byte for fp32)
 template <typename T> __device__ __forceinline__ float2 load_pair(const T* p);
 template <> __device__ __forceinline__ float2 load_pair<float>(const float* p) { return *reinterpret_cast<const float2*>(p); }

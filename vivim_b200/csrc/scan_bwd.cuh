@@ -44,6 +44,9 @@ constexpr int kBwdSlots = kSeg / 4;                    // float4 slots per state
 #ifndef VV_BWD_TRANSPOSE
 #define VV_BWD_TRANSPOSE 1
 #endif
+#ifndef VV_BWD_PACK_BC
+#define VV_BWD_PACK_BC 1
+#endif
 constexpr bool kBwdTranspose = VV_BWD_TRANSPOSE != 0;  // dB/dC over a warp's channels: shuffle reduce-scatter (1) or staggered smem RMW (0)
 
 static_assert(kSeg == 64, "a channel group is 8 lanes x 8 positions");
@@ -146,6 +149,7 @@ template <typename T, bool kVec, int NB, bool kGen, bool kTma = false>
 __global__ void __launch_bounds__(kBwdThreads, 4) seg_bwd_kernel(const vv_scan_args a, const __grid_constant__ BwdTmaMaps maps) {
     extern __shared__ __align__(128) float4 smem4[];
     __shared__ __align__(8) uint64_t tma_bar;
+    constexpr bool kPackBC = sizeof(T) == 2 && VV_BWD_PACK_BC != 0;
     const int L = a.seqlen, N = a.dstate;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int cg = lane >> 3, tb = lane & 7;
@@ -421,7 +425,27 @@ __global__ void __launch_bounds__(kBwdThreads, 4) seg_bwd_kernel(const vv_scan_a
             y2[jp] = fma2(cm2[jp], hs2[jp], y2[jp]);
         }
         dAs[n * 32 + ((lane + 8 * n) & 31)] = dA2.x + dA2.y;
-        if (kBwdTranspose) {
+        if (kBwdTranspose && kPackBC) {
+            // 16-bit I/O: dB / dC leave the kernel in that dtype anyway, so the 4-channel partial sums of the warp travel
+            // as packed pairs -- half the shuffles, selects and adds of the fp32 route below, and a 64-bit tile store.
+            uint32_t pB[4], pC[4], k2[4], k1[2];
+#pragma unroll
+            for (int jp = 0; jp < 4; ++jp) {
+                pB[jp] = pack_pair<T>(dB2[jp]);
+                pC[jp] = pack_pair<T>(dC2[jp]);
+            }
+#pragma unroll
+            for (int jp = 0; jp < 4; ++jp) {
+                const uint32_t send = hi16 ? pB[jp] : pC[jp], keep = hi16 ? pC[jp] : pB[jp];
+                k2[jp] = add_pairs<T>(keep, __shfl_xor_sync(0xffffffffu, send, 16));
+            }
+#pragma unroll
+            for (int jp = 0; jp < 2; ++jp) {
+                const uint32_t send = mid8 ? k2[jp] : k2[2 + jp], keep = mid8 ? k2[2 + jp] : k2[jp];
+                k1[jp] = add_pairs<T>(keep, __shfl_xor_sync(0xffffffffu, send, 8));
+            }
+            *reinterpret_cast<uint2*>(my_d + n * kBwdSlots) = make_uint2(k1[0], k1[1]);   // head of the fp32 route's slot
+        } else if (kBwdTranspose) {
             // reduce dB / dC over the 4 channels of the warp: transposing reduce-scatter.  Lanes 0-15 end
             // with dB, lanes 16-31 with dC; (lane & 8) selects the half of the lane's 8 positions.
             float2 k2[4];
@@ -540,7 +564,8 @@ __global__ void __launch_bounds__(kBwdThreads, 4) seg_bwd_kernel(const vv_scan_a
 #pragma unroll
             for (int w = 0; w < kBwdWarps; ++w) {
                 const float4 x = w0[w * bwd_warp_f4(NB) + tensor * (NB * kBwdSlots) + n * kBwdSlots + slot];
-                v = add4(v, make_float2(x.x, x.y), make_float2(x.z, x.w));
+                if (kPackBC) v = add4(v, unpack_pair<T>(__float_as_uint(x.x)), unpack_pair<T>(__float_as_uint(x.y)));
+                else v = add4(v, make_float2(x.x, x.y), make_float2(x.z, x.w));
             }
             const int t = t0s + pc * 4;
             if (n < N) {

@@ -107,12 +107,16 @@ class TemporalMambaBlock(nn.Module):
         self.drop_path_rate = float(drop_path)
         self.apply(_reference_init)
 
+    def forward_tokens(self, tokens, frames, height, width):
+        """(B, frames*H*W, C) -> same.  The arithmetic of MambaLayer.forward (modeling/vivim.py:147-159) without its
+        (B, C, T, H, W) <-> token transposes: the stage keeps the token layout across its blocks."""
+        tokens = tokens + _stochastic_depth(self.mamba(self.norm1(tokens)), self.drop_path_rate, self.training)
+        return tokens + _stochastic_depth(self.mlp(self.norm2(tokens), frames, height, width),
+                                          self.drop_path_rate, self.training)
+
     def forward(self, x):
         b, c, frames, height, width = x.shape
-        tokens = x.flatten(2).transpose(1, 2)
-        tokens = tokens + _stochastic_depth(self.mamba(self.norm1(tokens)), self.drop_path_rate, self.training)
-        tokens = tokens + _stochastic_depth(self.mlp(self.norm2(tokens), frames, height, width),
-                                            self.drop_path_rate, self.training)
+        tokens = self.forward_tokens(x.flatten(2).transpose(1, 2), frames, height, width)
         return tokens.transpose(1, 2).reshape(b, c, frames, height, width)
 
 
@@ -135,9 +139,12 @@ class _Encoder(nn.Module):
             tokens, height, width = embed(x)
             for blk in blocks:
                 tokens = blk(tokens, height, width, False)[0]
-            fmap = tokens.view(n, frames, height, width, -1).permute(0, 4, 1, 2, 3)   # (n, C, frames, H, W)
-            fmap = temporal(fmap.contiguous())
-            x = fmap.transpose(1, 2).flatten(0, 1)                                     # (n*frames, C, H, W)
+            # (n*frames, H*W, C) is already the clip's token sequence (frame-major): a view, where the reference goes
+            # through (n, C, frames, H, W) and back around every block (vivim.py:213-215, 147-159)
+            seq = tokens.reshape(n, frames * height * width, -1)
+            for wrapped in temporal:
+                seq = wrapped[0].forward_tokens(seq, frames, height, width)
+            x = seq.view(n * frames, height, width, -1).permute(0, 3, 1, 2).contiguous()   # (n*frames, C, H, W)
             features.append(x)
         return features
 
