@@ -20,6 +20,8 @@ CASES = [
     (7, 100, torch.float32, torch.float32),             # channels % 4 != 0: element-wise path
     (33, 36, torch.float16, torch.float16),
     (1, 512, torch.float32, torch.float16),
+    (5, 32, torch.float32, torch.float32),              # 8 lanes per row: four rows per warp, the last trip partly empty
+    (1027, 64, torch.bfloat16, torch.bfloat16),         # 16 lanes per row, odd row count
 ]
 
 

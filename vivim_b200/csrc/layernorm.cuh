@@ -64,11 +64,21 @@ template <> struct LnVec<__half, 4> {
     }
 };
 
-// Lane `lane` owns the V-element groups g = lane + 32 k (k < K) of a row, i.e. channels [g V, g V + V); groups beyond
+// sum over the LPR (8, 16 or 32) adjacent lanes that share a row
+template <int LPR>
+__device__ __forceinline__ float row_sum(float v) {
+#pragma unroll
+    for (int o = LPR / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// LPR lanes share a row (LPR < 32 only with K = 1: a 64-channel row is 16 groups of 4, so a warp serves two rows at a
+// time instead of idling half of its lanes).  Lane `lane` of the row owns the V-element groups g = lane + 32 k (k < K) of a row, i.e. channels [g V, g V + V); groups beyond
 // the row (g V >= C) are padding.  Vivim: C = 64 / 128 / 320 / 512 -> (V, K) = (4, 1) / (4, 1) / (4, 4) / (4, 4).
-template <typename TI, typename TO, int V, int K>
+template <typename TI, typename TO, int V, int K, int LPR>
 __global__ void __launch_bounds__(kLnThreads) layernorm_fwd_kernel(const vv_layernorm_args a) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    constexpr int RPW = 32 / LPR;                 // rows per warp
+    const int lane = (threadIdx.x & 31) % LPR, warp = (threadIdx.x >> 5) * RPW + (threadIdx.x & 31) / LPR;
     const int C = a.channels;
     const float inv_c = 1.f / (float)C;
     float w[K][V], bsh[K][V];
@@ -76,18 +86,22 @@ __global__ void __launch_bounds__(kLnThreads) layernorm_fwd_kernel(const vv_laye
     for (int k = 0; k < K; ++k)
 #pragma unroll
         for (int i = 0; i < V; ++i) {
-            const int c = (lane + 32 * k) * V + i;
+            const int c = (lane + LPR * k) * V + i;
             w[k][i] = (a.weight && c < C) ? a.weight[c] : 1.f;
             bsh[k][i] = (a.bias && c < C) ? a.bias[c] : 0.f;
         }
-    for (int64_t row = (int64_t)blockIdx.x * kLnWarps + warp; row < a.rows; row += (int64_t)gridDim.x * kLnWarps) {
-        const TI* x = reinterpret_cast<const TI*>(a.x) + row * a.x_rs;
+    // every lane of a warp makes the same number of trips (the row sums are full-mask shuffles): the rows of a trip that
+    // do not exist are computed on zeros and not stored
+    for (int64_t row0 = (int64_t)blockIdx.x * kLnWarps * RPW; row0 < a.rows; row0 += (int64_t)gridDim.x * kLnWarps * RPW) {
+        const int64_t row = row0 + warp;
+        const bool valid = row < a.rows;
+        const TI* x = reinterpret_cast<const TI*>(a.x) + (valid ? row : 0) * a.x_rs;
         float v[K][V];
         float sum = 0.f;
 #pragma unroll
         for (int k = 0; k < K; ++k) {
-            const int c0 = (lane + 32 * k) * V;
-            if (c0 < C) LnVec<TI, V>::load(x + c0, v[k]);
+            const int c0 = (lane + LPR * k) * V;
+            if (c0 < C && valid) LnVec<TI, V>::load(x + c0, v[k]);
             else {
 #pragma unroll
                 for (int i = 0; i < V; ++i) v[k][i] = 0.f;
@@ -95,28 +109,28 @@ __global__ void __launch_bounds__(kLnThreads) layernorm_fwd_kernel(const vv_laye
 #pragma unroll
             for (int i = 0; i < V; ++i) sum += v[k][i];
         }
-        const float mean = warp_sum(sum) * inv_c;
+        const float mean = row_sum<LPR>(sum) * inv_c;
         float sq = 0.f;
 #pragma unroll
         for (int k = 0; k < K; ++k)
 #pragma unroll
             for (int i = 0; i < V; ++i) {
-                const float dlt = ((lane + 32 * k) * V + i < C) ? v[k][i] - mean : 0.f;
+                const float dlt = ((lane + LPR * k) * V + i < C) ? v[k][i] - mean : 0.f;
                 sq = fmaf(dlt, dlt, sq);
             }
-        const float rstd = rsqrtf(warp_sum(sq) * inv_c + a.eps);
-        TO* out = reinterpret_cast<TO*>(a.out) + row * a.out_rs;
+        const float rstd = rsqrtf(row_sum<LPR>(sq) * inv_c + a.eps);
+        TO* out = reinterpret_cast<TO*>(a.out) + (valid ? row : 0) * a.out_rs;
 #pragma unroll
         for (int k = 0; k < K; ++k) {
-            const int c0 = (lane + 32 * k) * V;
-            if (c0 < C) {
+            const int c0 = (lane + LPR * k) * V;
+            if (c0 < C && valid) {
                 float o[V];
 #pragma unroll
                 for (int i = 0; i < V; ++i) o[i] = fmaf((v[k][i] - mean) * rstd, w[k][i], bsh[k][i]);
                 LnVec<TO, V>::store(out + c0, o);
             }
         }
-        if (lane == 0) {
+        if (lane == 0 && valid) {
             a.mean[row] = mean;
             a.rstd[row] = rstd;
         }
@@ -124,10 +138,11 @@ __global__ void __launch_bounds__(kLnThreads) layernorm_fwd_kernel(const vv_laye
 }
 
 // dx = rstd (g w - mean(g w) - xhat mean(g w xhat));  dweight += sum_rows g xhat;  dbias += sum_rows g
-template <typename TI, typename TO, int V, int K>
+template <typename TI, typename TO, int V, int K, int LPR>
 __global__ void __launch_bounds__(kLnThreads) layernorm_bwd_kernel(const vv_layernorm_args a) {
-    __shared__ float red[2][kLnWarps][32 * K * V + 1];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    constexpr int RPW = 32 / LPR;
+    __shared__ float red[2][kLnWarps * RPW][LPR * K * V + 1];
+    const int lane = (threadIdx.x & 31) % LPR, warp = (threadIdx.x >> 5) * RPW + (threadIdx.x & 31) / LPR;
     const int C = a.channels;
     const float inv_c = 1.f / (float)C;
     float w[K][V], pw[K][V], pb[K][V];
@@ -135,21 +150,23 @@ __global__ void __launch_bounds__(kLnThreads) layernorm_bwd_kernel(const vv_laye
     for (int k = 0; k < K; ++k)
 #pragma unroll
         for (int i = 0; i < V; ++i) {
-            const int c = (lane + 32 * k) * V + i;
+            const int c = (lane + LPR * k) * V + i;
             w[k][i] = (a.weight && c < C) ? a.weight[c] : 1.f;
             pw[k][i] = pb[k][i] = 0.f;
         }
-    for (int64_t row = (int64_t)blockIdx.x * kLnWarps + warp; row < a.rows; row += (int64_t)gridDim.x * kLnWarps) {
-        const TI* x = reinterpret_cast<const TI*>(a.x) + row * a.x_rs;
-        const TO* g = reinterpret_cast<const TO*>(a.dout) + row * a.dout_rs;
-        const float mean = a.mean[row], rstd = a.rstd[row];
+    for (int64_t row0 = (int64_t)blockIdx.x * kLnWarps * RPW; row0 < a.rows; row0 += (int64_t)gridDim.x * kLnWarps * RPW) {
+        const int64_t row = row0 + warp;
+        const bool valid = row < a.rows;
+        const TI* x = reinterpret_cast<const TI*>(a.x) + (valid ? row : 0) * a.x_rs;
+        const TO* g = reinterpret_cast<const TO*>(a.dout) + (valid ? row : 0) * a.dout_rs;
+        const float mean = valid ? a.mean[row] : 0.f, rstd = valid ? a.rstd[row] : 0.f;
         float xh[K][V], gw[K][V];
         float s1 = 0.f, s2 = 0.f;
 #pragma unroll
         for (int k = 0; k < K; ++k) {
-            const int c0 = (lane + 32 * k) * V;
+            const int c0 = (lane + LPR * k) * V;
             float gv[V];
-            if (c0 < C) {
+            if (c0 < C && valid) {
                 LnVec<TI, V>::load(x + c0, xh[k]);
                 LnVec<TO, V>::load(g + c0, gv);
             } else {
@@ -166,13 +183,13 @@ __global__ void __launch_bounds__(kLnThreads) layernorm_bwd_kernel(const vv_laye
                 pb[k][i] += gv[i];
             }
         }
-        s1 = warp_sum(s1) * inv_c;
-        s2 = warp_sum(s2) * inv_c;
-        if (a.dx) {
+        s1 = row_sum<LPR>(s1) * inv_c;
+        s2 = row_sum<LPR>(s2) * inv_c;
+        if (a.dx && valid) {
             TI* dx = reinterpret_cast<TI*>(a.dx) + row * a.dx_rs;
 #pragma unroll
             for (int k = 0; k < K; ++k) {
-                const int c0 = (lane + 32 * k) * V;
+                const int c0 = (lane + LPR * k) * V;
                 if (c0 < C) {
                     float o[V];
 #pragma unroll
@@ -183,19 +200,19 @@ __global__ void __launch_bounds__(kLnThreads) layernorm_bwd_kernel(const vv_laye
         }
     }
     if (a.dweight == nullptr && a.dbias == nullptr) return;
-    // ---- fold the 8 warps' partial sums, one atomic per channel and CTA
+    // ---- fold the partial sums of the CTA's (sub-)warps, one atomic per channel and CTA
 #pragma unroll
     for (int k = 0; k < K; ++k)
 #pragma unroll
         for (int i = 0; i < V; ++i) {
-            red[0][warp][(lane + 32 * k) * V + i] = pw[k][i];
-            red[1][warp][(lane + 32 * k) * V + i] = pb[k][i];
+            red[0][warp][(lane + LPR * k) * V + i] = pw[k][i];
+            red[1][warp][(lane + LPR * k) * V + i] = pb[k][i];
         }
     __syncthreads();
     for (int c = threadIdx.x; c < C; c += kLnThreads) {
         float sw = 0.f, sb = 0.f;
 #pragma unroll
-        for (int wv = 0; wv < kLnWarps; ++wv) {
+        for (int wv = 0; wv < kLnWarps * RPW; ++wv) {
             sw += red[0][wv][c];
             sb += red[1][wv][c];
         }

@@ -197,25 +197,30 @@ int launch_conv_dirs(const vv_conv1d_dirs_args* a, void* stream) {
 // ---------------------------------------------------------------- LayerNorm dispatch
 template <typename TI, typename TO, int V, bool kBwd>
 int launch_ln_k(const vv_layernorm_args& a, int K, cudaStream_t st) {
-    const int64_t want = (a.rows + vv::kLnWarps - 1) / vv::kLnWarps;
-    // forward: one row per warp and trip; backward: few enough CTAs that the per-CTA channel atomics stay cheap
+    const int groups = (a.channels + V - 1) / V;               // V-element groups per row
+    const int lpr = (V == 4 && groups <= 8) ? 8 : (V == 4 && groups <= 16) ? 16 : 32;
+    const int rows_per_cta = vv::kLnWarps * (32 / lpr);
+    const int64_t want = (a.rows + rows_per_cta - 1) / rows_per_cta;
+    // forward: one row per (sub-)warp and trip; backward: few enough CTAs that the per-CTA channel atomics stay cheap
     const unsigned grid = (unsigned)std::max<int64_t>(1, std::min<int64_t>(want, (int64_t)sm_count() * (kBwd ? 4 : 16)));
-#define VV_LN_LAUNCH(KK)                                                                                   \
+#define VV_LN_LAUNCH(KK, LPR)                                                                              \
     do {                                                                                                   \
-        if (kBwd) vv::layernorm_bwd_kernel<TI, TO, V, KK><<<grid, vv::kLnThreads, 0, st>>>(a);             \
-        else vv::layernorm_fwd_kernel<TI, TO, V, KK><<<grid, vv::kLnThreads, 0, st>>>(a);                  \
+        if (kBwd) vv::layernorm_bwd_kernel<TI, TO, V, KK, LPR><<<grid, vv::kLnThreads, 0, st>>>(a);        \
+        else vv::layernorm_fwd_kernel<TI, TO, V, KK, LPR><<<grid, vv::kLnThreads, 0, st>>>(a);             \
     } while (0)
     if constexpr (V == 4) {
-        switch (K) {
-            case 1: VV_LN_LAUNCH(1); break;
-            case 2: VV_LN_LAUNCH(2); break;
-            case 3: VV_LN_LAUNCH(3); break;
-            default: VV_LN_LAUNCH(4); break;
+        if (lpr == 8) VV_LN_LAUNCH(1, 8);
+        else if (lpr == 16) VV_LN_LAUNCH(1, 16);
+        else switch (K) {
+            case 1: VV_LN_LAUNCH(1, 32); break;
+            case 2: VV_LN_LAUNCH(2, 32); break;
+            case 3: VV_LN_LAUNCH(3, 32); break;
+            default: VV_LN_LAUNCH(4, 32); break;
         }
     } else {
-        if (K <= 4) VV_LN_LAUNCH(4);
-        else if (K <= 8) VV_LN_LAUNCH(8);
-        else VV_LN_LAUNCH(16);
+        if (K <= 4) VV_LN_LAUNCH(4, 32);
+        else if (K <= 8) VV_LN_LAUNCH(8, 32);
+        else VV_LN_LAUNCH(16, 32);
     }
 #undef VV_LN_LAUNCH
     return check_launch(kBwd ? "layernorm_bwd_kernel" : "layernorm_fwd_kernel");
