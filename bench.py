@@ -626,6 +626,8 @@ def bench_e2e(clips, ndirs, steps, world, device, torch, dist, lib):
     ev_cmp = [torch.cuda.Event() for _ in range(depth)]
     ev_out = [torch.cuda.Event() for _ in range(depth)]
 
+    kernels_on = [True]
+
     def one(i):
         k = i % depth
         with torch.cuda.stream(s_in):
@@ -635,7 +637,8 @@ def bench_e2e(clips, ndirs, steps, world, device, torch, dist, lib):
         with torch.cuda.stream(s_cmp):
             s_cmp.wait_event(ev_in[k])
             s_cmp.wait_event(ev_out[k])             # the previous results of this slot have left the device
-            launch_step(sets[k], lib, s_cmp.cuda_stream)
+            if kernels_on[0]:
+                launch_step(sets[k], lib, s_cmp.cuda_stream)
             ev_cmp[k].record(s_cmp)
         with torch.cuda.stream(s_out):
             s_out.wait_event(ev_cmp[k])
@@ -668,10 +671,17 @@ def bench_e2e(clips, ndirs, steps, world, device, torch, dist, lib):
     # scheduling hiccup on the box)
     blocks = sorted(block() for _ in range(3))
     elapsed = max_over_ranks(blocks[1], device)
+    # the same copies WITHOUT the kernels: what the host link of this box gives `world` ranks at once (attributes the
+    # e2e figure to PCIe / host memory when N ranks share one host)
+    kernels_on[0] = False
+    copies_only = max_over_ranks(sorted(block() for _ in range(3))[1], device)
+    kernels_on[0] = True
     fwd_b, bwd_b = algo_bytes(clips * ndirs)
     return {"value": aggregate_throughput((fwd_b + bwd_b) * steps, world, elapsed) / 1e9, "unit": "GB/s", "h2d_bytes_per_step": h2d,
             "d2h_bytes_per_step": d2h, "steps": steps, "ms_per_step": elapsed / steps * 1e3,
             "ms_per_step_blocks": [b / steps * 1e3 for b in blocks],
+            "copies_only_ms_per_step": copies_only / steps * 1e3,
+            "copies_only_GBps_per_rank_each_way": max(h2d, d2h) / (copies_only / steps) / 1e9,
             "pcie_floor_ms": max(h2d, d2h) / 55e9 * 1e3,
             "api": "vivim_b200.selective_scan_cuda fwd + bwd (vv_scan_fwd / vv_scan_bwd, include/vivim_b200.h) on caller-owned "
                    "device buffers, inputs from / results to pinned host memory every step",

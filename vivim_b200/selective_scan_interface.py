@@ -184,8 +184,11 @@ def _project(conv_out, x_proj_weight, delta_proj_weight, A, B, C, B_proj_bias, C
             return _as_groups(M, conv_out, A, name)
         cols = x_dbl[:, lo:hi]
         if proj_bias is not None:
-            cols = cols + proj_bias.to(cols.dtype)
-        return cols.reshape(batch, L, dstate).transpose(1, 2).contiguous().unsqueeze(1), "proj"  # (b,1,n,l)
+            cols = (cols + proj_bias.to(cols.dtype)).reshape(batch, L, dstate).transpose(1, 2).contiguous().unsqueeze(1)
+            return cols, "proj"
+        # No copy: a (b, 1, n, l) VIEW of x_dbl's columns (state stride 1, sequence stride R+2N) -- the kernels read B / C
+        # from the rows of the GEMM output where the reference transposes them (selective_scan_interface.py:187-207)
+        return cols.unflatten(0, (batch, L)).permute(0, 2, 1).unsqueeze(1), "proj"
 
     Bm, kind_B = pick(B, rank, rank + dstate, B_proj_bias, "B")
     Cm, kind_C = pick(C, x_dbl.shape[1] - dstate, x_dbl.shape[1], C_proj_bias, "C")
@@ -266,31 +269,44 @@ class _MambaInner(torch.autograd.Function):
         # dx and dz are written next to each other so that no torch.cat is needed
         dxz = torch.empty_like(xz)
         dx, dz = dxz.chunk(2, dim=1)
-        dconv, ddelta, dA, dB, dC, dD, ddelta_bias, dz = selective_scan_cuda.bwd(
-            conv_out, delta, A, Bm, Cm, D, z, delta_bias, dout_y, chk, dz, ctx.delta_softplus)
         dx_dbl = torch.empty_like(x_dbl)
+        both_proj = ctx.kind_B == "proj" and ctx.kind_C == "proj"
+        dBC_out = None
+        if both_proj:
+            # dB / dC land straight in their column blocks of dx_dbl (the cast kernel of vv_scan_bwd writes them there):
+            # no rearrange + slice copy (selective_scan_interface.py:255-271)
+            cols = lambda lo, hi: dx_dbl[:, lo:hi].unflatten(0, (batch, L)).permute(0, 2, 1).unsqueeze(1)  # noqa: E731
+            dBC_out = (cols(rank, rank + dstate), cols(x_dbl.shape[1] - dstate, x_dbl.shape[1]))
+        dconv, ddelta, dA, dB, dC, dD, ddelta_bias, dz = selective_scan_cuda.bwd(
+            conv_out, delta, A, Bm, Cm, D, z, delta_bias, dout_y, chk, dz, ctx.delta_softplus, dBC_out=dBC_out)
         dB_out = dC_out = dB_proj_bias = dC_proj_bias = None
-        if ctx.kind_B == "proj":
-            dBf = dB.squeeze(1).transpose(1, 2).reshape(batch * L, dstate)
-            dB_proj_bias = dBf.sum(0) if ctx.has_B_bias else None
-            dx_dbl[:, rank:rank + dstate] = dBf
+        if both_proj:
+            dB_proj_bias = dx_dbl[:, rank:rank + dstate].sum(0) if ctx.has_B_bias else None
+            dC_proj_bias = dx_dbl[:, -dstate:].sum(0) if ctx.has_C_bias else None
         else:
-            dB_out = _ungroup_grad(dB, ctx.kind_B)
-            dx_dbl[:, rank:rank + dstate] = 0
-        if ctx.kind_C == "proj":
-            dCf = dC.squeeze(1).transpose(1, 2).reshape(batch * L, dstate)
-            dC_proj_bias = dCf.sum(0) if ctx.has_C_bias else None
-            dx_dbl[:, -dstate:] = dCf
-        else:
-            dC_out = _ungroup_grad(dC, ctx.kind_C)
-            dx_dbl[:, -dstate:] = 0
+            if ctx.kind_B == "proj":
+                dBf = dB.squeeze(1).transpose(1, 2).reshape(batch * L, dstate)
+                dB_proj_bias = dBf.sum(0) if ctx.has_B_bias else None
+                dx_dbl[:, rank:rank + dstate] = dBf
+            else:
+                dB_out = _ungroup_grad(dB, ctx.kind_B)
+                dx_dbl[:, rank:rank + dstate] = 0
+            if ctx.kind_C == "proj":
+                dCf = dC.squeeze(1).transpose(1, 2).reshape(batch * L, dstate)
+                dC_proj_bias = dCf.sum(0) if ctx.has_C_bias else None
+                dx_dbl[:, -dstate:] = dCf
+            else:
+                dC_out = _ungroup_grad(dC, ctx.kind_C)
+                dx_dbl[:, -dstate:] = 0
         ddelta_f = ddelta.transpose(0, 1).reshape(dim, batch * L)                     # (d, b l)
         ddelta_proj_weight = ddelta_f @ x_dbl[:, :rank]
         dx_dbl[:, :rank] = ddelta_f.t() @ delta_proj_weight
         conv_flat = conv_out.transpose(1, 2).reshape(batch * L, dim)                  # (b l, d)
         dx_proj_weight = dx_dbl.t() @ conv_flat
-        # dconv (b, d, l) += (dx_dbl @ x_proj_weight) laid out as (b, l, d)
-        dconv = dconv + (dx_dbl @ x_proj_weight).view(batch, L, dim).transpose(1, 2)
+        # dconv (b, d, l) += x_proj_weight^T (d, R+2N) @ dx_dbl^T (R+2N, l), per batch entry, accumulated in place in the
+        # kernels' (b, d, l) layout (no (b, l, d) intermediate and transposing add)
+        dconv.baddbmm_(x_proj_weight.t().unsqueeze(0).expand(batch, -1, -1),
+                       dx_dbl.view(batch, L, -1).transpose(1, 2))
         dx, dconv_w, dconv_b = causal_conv1d_cuda.causal_conv1d_bwd(x, conv_w, conv_b, dconv, dx, True)
         return (dxz, dconv_w.unsqueeze(1), dconv_b, dx_proj_weight, ddelta_proj_weight,
                 dout_proj_weight, dout_proj_bias, dA, dB_out, dC_out, dD, ddelta_bias,
