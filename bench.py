@@ -433,7 +433,8 @@ def run_ours(args, rank, world, local_rank):
         barrier()
     elapsed = max_over_ranks(elapsed, device)
     value = aggregate_throughput((fwd_b + bwd_b) * args.steps, world, elapsed) / 1e9
-    launches = 7 * args.steps
+    timed_launches = 7 * args.steps       # per rank: 3 forward + 4 backward kernels of libvivim_b200.so per timed step
+    launches = timed_launches
 
     # ---- the six kernels one by one (pass mask), rotating sets, CUDA events on the launch stream
     stream = torch.cuda.current_stream().cuda_stream
@@ -538,7 +539,8 @@ def run_ours(args, rank, world, local_rank):
             "us_per_direction_scan": elapsed / args.steps / (clips * ndirs) * 1e6,
             "bytes_algorithmic_per_step": fwd_b + bwd_b, "bytes_compulsory_per_step": cf + cb,
             "hbm_frac_of_measured_peak": value / world / peak,
-            "roofline": roofline, "e2e": e2e, "gpu_launches": launches, "clocks": clk.summary(),
+            "roofline": roofline, "e2e": e2e, "gpu_launches": timed_launches, "gpu_launches_whole_run": launches,
+            "clocks": clk.summary(),
             "kernel_us": {k: v * 1e6 for k, v in passes.items()},
             "walking_passes": {"fwd": 2, "bwd": 2,
                                "note": "decays are evaluated once per (channel, token, state) in each of: forward aggregate, "
