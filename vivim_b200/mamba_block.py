@@ -61,7 +61,13 @@ class MambaDirsFn(torch.autograd.Function):
         x, z = xz[:, :Dn], xz[:, Dn:]
         cw = torch.stack([w.reshape(Dn, -1).float() for w in conv_w])        # (nd, D, K)
         cb = torch.stack([b.float() for b in conv_b]) if has_conv_b else None
+        # x_proj weights, rows padded with zeros to a multiple of 8 (R + 2N = 36 at stage 1, 52 at stage 3): rows of x_dbl
+        # then start 16-byte aligned, without which cuBLAS falls back to its `align2` WMMA kernels for every GEMM that
+        # touches x_dbl / dx_dbl (190 + 180 us of a 1.15 ms block at stage 1, profiles/r02_block.md)
+        R2p = -(-R2 // 8) * 8
         xw = torch.stack([cast(w) for w in xp_w])                            # (nd, R2, D)
+        if R2p != R2:
+            xw = torch.cat([xw, xw.new_zeros(nd, R2p - R2, Dn)], dim=1)      # (nd, R2p, D)
         dw = torch.stack([cast(w) for w in dt_w])                            # (nd, D, R)
         A_all = torch.cat([a.float() for a in A]).contiguous()               # (nd*D, N)
         D_all = torch.cat([d.float() for d in Dp]).contiguous()
@@ -71,7 +77,7 @@ class MambaDirsFn(torch.autograd.Function):
         x_dbl = torch.matmul(co4.transpose(-1, -2), xw.transpose(-1, -2))    # (B, nd, L, R2)
         delta = torch.matmul(dw, x_dbl[..., :R].transpose(-1, -2)).view(B_, nd * Dn, L)
         Bv = x_dbl[..., R:R + N].permute(0, 1, 3, 2)                         # (B, nd, N, L) views, dstate stride 1
-        Cv = x_dbl[..., R + N:].permute(0, 1, 3, 2)
+        Cv = x_dbl[..., R + N:R2].permute(0, 1, 3, 2)
         _, chk, _, out_z = selective_scan_cuda.fwd(conv_out, delta, A_all, Bv, Cv, D_all, z, b_all, True,
                                                    want_out=False, dirs=dirs, nframes=nframes)
         w3 = (out_wc * scale).repeat(1, nd)                                  # (E, nd*D): scaled sum over the directions
@@ -104,13 +110,16 @@ class MambaDirsFn(torch.autograd.Function):
         conv_out = causal_conv1d_cuda.causal_conv1d_dirs_fwd(x, cw, cb, dirs, nframes, True)
         co4 = conv_out.view(B_, nd, Dn, L)
         delta = torch.matmul(dw, x_dbl[..., :R].transpose(-1, -2)).view(B_, nd * Dn, L)
+        R2 = R + 2 * N
         Bv = x_dbl[..., R:R + N].permute(0, 1, 3, 2)
-        Cv = x_dbl[..., R + N:].permute(0, 1, 3, 2)
+        Cv = x_dbl[..., R + N:R2].permute(0, 1, 3, 2)
         # ---- scan backward: dz of every direction next to dx; dB / dC straight into dx_dbl
         dxz = torch.empty((B_, (1 + nd) * Dn, L), dtype=xz.dtype, device=xz.device)
         dx_dbl = torch.empty_like(x_dbl)
+        if dx_dbl.shape[-1] != R2:
+            dx_dbl[..., R2:] = 0                                             # the padding columns meet zero weight rows
         dBv = dx_dbl[..., R:R + N].permute(0, 1, 3, 2)
-        dCv = dx_dbl[..., R + N:].permute(0, 1, 3, 2)
+        dCv = dx_dbl[..., R + N:R2].permute(0, 1, 3, 2)
         dconv, ddelta, dA, _, _, dD, ddt_b, _ = selective_scan_cuda.bwd(
             conv_out, delta, A_all, Bv, Cv, D_all, z, b_all, g, chk, dxz[:, Dn:], True,
             dirs=dirs, nframes=nframes, dBC_out=(dBv, dCv))
@@ -136,7 +145,7 @@ class MambaDirsFn(torch.autograd.Function):
         K = cw.shape[2]
         grads = ([d_cw[k].view(Dn, 1, K) for k in range(nd)]
                  + [d_cb[k] if ctx.has_conv_b else None for k in range(nd)]
-                 + [d_xw[k] for k in range(nd)] + [d_dw[k] for k in range(nd)]
+                 + [d_xw[k, :R2] for k in range(nd)] + [d_dw[k] for k in range(nd)]
                  + [dA[k * Dn:(k + 1) * Dn] for k in range(nd)] + [dD[k * Dn:(k + 1) * Dn] for k in range(nd)]
                  + [ddt_b[k * Dn:(k + 1) * Dn] for k in range(nd)])
         return (d_hidden, d_in_w, d_in_b, d_out_w, d_out_b, None, None, None, None, *grads)
