@@ -61,30 +61,35 @@ class MambaDirsFn(torch.autograd.Function):
         x, z = xz[:, :Dn], xz[:, Dn:]
         cw = torch.stack([w.reshape(Dn, -1).float() for w in conv_w])        # (nd, D, K)
         cb = torch.stack([b.float() for b in conv_b]) if has_conv_b else None
-        # x_proj weights, rows padded with zeros to a multiple of 8 (R + 2N = 36 at stage 1, 52 at stage 3): rows of x_dbl
-        # then start 16-byte aligned, without which cuBLAS falls back to its `align2` WMMA kernels for every GEMM that
-        # touches x_dbl / dx_dbl (190 + 180 us of a 1.15 ms block at stage 1, profiles/r02_block.md)
-        R2p = -(-R2 // 8) * 8
-        xw = torch.stack([cast(w) for w in xp_w])                            # (nd, R2, D)
-        if R2p != R2:
-            xw = torch.cat([xw, xw.new_zeros(nd, R2p - R2, Dn)], dim=1)      # (nd, R2p, D)
-        dw = torch.stack([cast(w) for w in dt_w])                            # (nd, D, R)
+        # Column layout of x_dbl: [dt (R) | zeros to Rp | B (N) | C (N) | zeros to R2p], Rp and R2p multiples of 8.  With the
+        # reference's packed (R + 2N = 36 at stage 1, 52 at stage 3) rows every GEMM that touches x_dbl / dx_dbl or the
+        # R-wide dt block runs on 4-byte aligned operands and cuBLAS falls back to its `align2` WMMA kernels (190 + 180 us
+        # of a 1.15 ms block at stage 1, profiles/r02_block.md).  The padding meets zero weight rows / columns.
+        Rp = -(-R // 8) * 8
+        R2p = -(-(Rp + 2 * N) // 8) * 8
+        xw = xz.new_zeros(nd, R2p, Dn)                                       # (nd, R2p, D)
+        for k, w in enumerate(xp_w):
+            xw[k, :R] = w[:R]
+            xw[k, Rp:Rp + 2 * N] = w[R:]
+        dw = xz.new_zeros(nd, Dn, Rp)                                        # (nd, D, Rp)
+        for k, w in enumerate(dt_w):
+            dw[k, :, :R] = w
         A_all = torch.cat([a.float() for a in A]).contiguous()               # (nd*D, N)
         D_all = torch.cat([d.float() for d in Dp]).contiguous()
         b_all = torch.cat([b.float() for b in dt_b]).contiguous()
         conv_out = causal_conv1d_cuda.causal_conv1d_dirs_fwd(x, cw, cb, dirs, nframes, True)   # (B, nd*D, L)
         co4 = conv_out.view(B_, nd, Dn, L)
-        x_dbl = torch.matmul(co4.transpose(-1, -2), xw.transpose(-1, -2))    # (B, nd, L, R2)
-        delta = torch.matmul(dw, x_dbl[..., :R].transpose(-1, -2)).view(B_, nd * Dn, L)
-        Bv = x_dbl[..., R:R + N].permute(0, 1, 3, 2)                         # (B, nd, N, L) views, dstate stride 1
-        Cv = x_dbl[..., R + N:R2].permute(0, 1, 3, 2)
+        x_dbl = torch.matmul(co4.transpose(-1, -2), xw.transpose(-1, -2))    # (B, nd, L, R2p)
+        delta = torch.matmul(dw, x_dbl[..., :Rp].transpose(-1, -2)).view(B_, nd * Dn, L)
+        Bv = x_dbl[..., Rp:Rp + N].permute(0, 1, 3, 2)                       # (B, nd, N, L) views, dstate stride 1
+        Cv = x_dbl[..., Rp + N:Rp + 2 * N].permute(0, 1, 3, 2)
         _, chk, _, out_z = selective_scan_cuda.fwd(conv_out, delta, A_all, Bv, Cv, D_all, z, b_all, True,
                                                    want_out=False, dirs=dirs, nframes=nframes)
         w3 = (out_wc * scale).repeat(1, nd)                                  # (E, nd*D): scaled sum over the directions
         out = _bmm_shared(out_z.transpose(1, 2), w3.t())                     # (B, L, E)
         if out_b is not None:
             out = out + cast(out_b)
-        ctx.dirs, ctx.nframes, ctx.nd, ctx.scale = dirs, nframes, nd, scale
+        ctx.dirs, ctx.nframes, ctx.nd, ctx.scale, ctx.rank = dirs, nframes, nd, scale, R
         ctx.has_in_b, ctx.has_out_b, ctx.has_conv_b = in_b is not None, out_b is not None, has_conv_b
         ctx.save_for_backward(hid, xz, x_dbl, chk, out_z, in_wc, out_wc, cw, cb, xw, dw, A_all, D_all, b_all)
         return out
@@ -96,7 +101,7 @@ class MambaDirsFn(torch.autograd.Function):
         dirs, nframes, nd, scale = ctx.dirs, ctx.nframes, ctx.nd, ctx.scale
         B_, two_d, L = xz.shape
         Dn = two_d // 2
-        R = dw.shape[2]
+        R, Rp = ctx.rank, dw.shape[2]
         N = A_all.shape[1]
         E = hid.shape[1]
         x, z = xz[:, :Dn], xz[:, Dn:]
@@ -109,25 +114,25 @@ class MambaDirsFn(torch.autograd.Function):
         # ---- recompute (checkpoint_lvl = 1: selective_scan_interface.py:238-241)
         conv_out = causal_conv1d_cuda.causal_conv1d_dirs_fwd(x, cw, cb, dirs, nframes, True)
         co4 = conv_out.view(B_, nd, Dn, L)
-        delta = torch.matmul(dw, x_dbl[..., :R].transpose(-1, -2)).view(B_, nd * Dn, L)
-        R2 = R + 2 * N
-        Bv = x_dbl[..., R:R + N].permute(0, 1, 3, 2)
-        Cv = x_dbl[..., R + N:R2].permute(0, 1, 3, 2)
+        delta = torch.matmul(dw, x_dbl[..., :Rp].transpose(-1, -2)).view(B_, nd * Dn, L)
+        Bv = x_dbl[..., Rp:Rp + N].permute(0, 1, 3, 2)
+        Cv = x_dbl[..., Rp + N:Rp + 2 * N].permute(0, 1, 3, 2)
         # ---- scan backward: dz of every direction next to dx; dB / dC straight into dx_dbl
         dxz = torch.empty((B_, (1 + nd) * Dn, L), dtype=xz.dtype, device=xz.device)
         dx_dbl = torch.empty_like(x_dbl)
-        if dx_dbl.shape[-1] != R2:
-            dx_dbl[..., R2:] = 0                                             # the padding columns meet zero weight rows
-        dBv = dx_dbl[..., R:R + N].permute(0, 1, 3, 2)
-        dCv = dx_dbl[..., R + N:R2].permute(0, 1, 3, 2)
+        if dx_dbl.shape[-1] != Rp + 2 * N:
+            dx_dbl[..., Rp + 2 * N:] = 0                                     # trailing padding (the dt padding is written below)
+        dBv = dx_dbl[..., Rp:Rp + N].permute(0, 1, 3, 2)
+        dCv = dx_dbl[..., Rp + N:Rp + 2 * N].permute(0, 1, 3, 2)
         dconv, ddelta, dA, _, _, dD, ddt_b, _ = selective_scan_cuda.bwd(
             conv_out, delta, A_all, Bv, Cv, D_all, z, b_all, g, chk, dxz[:, Dn:], True,
             dirs=dirs, nframes=nframes, dBC_out=(dBv, dCv))
         # ---- dt_proj / x_proj (selective_scan_interface.py:272-277), batched over the directions
         dd4 = ddelta.view(B_, nd, Dn, L)
-        d_dw = torch.matmul(dd4, x_dbl[..., :R]).sum(0)                                          # (nd, D, R)
-        dx_dbl[..., :R] = torch.matmul(dd4.transpose(-1, -2), dw)                                # (B, nd, L, R)
-        d_xw = torch.matmul(dx_dbl.transpose(-1, -2), co4.transpose(-1, -2)).sum(0)              # (nd, R2, D)
+        d_dw = torch.matmul(dd4, x_dbl[..., :Rp]).sum(0)                                         # (nd, D, Rp)
+        dx_dbl[..., :Rp] = torch.matmul(dd4.transpose(-1, -2), dw)                               # (B, nd, L, Rp): zeros beyond R
+        d_xw = torch.matmul(dx_dbl.transpose(-1, -2), co4.transpose(-1, -2)).sum(0)              # (nd, R2p, D)
+        d_xw = torch.cat([d_xw[:, :R], d_xw[:, Rp:Rp + 2 * N]], dim=1)                           # (nd, R + 2N, D)
         dconv4 = dconv.view(B_ * nd, Dn, L)
         dconv4.baddbmm_(xw.transpose(-1, -2).unsqueeze(0).expand(B_, -1, -1, -1).reshape(B_ * nd, Dn, -1),
                         dx_dbl.view(B_ * nd, L, -1).transpose(-1, -2))                           # += W_x^T dx_dbl^T
@@ -145,7 +150,7 @@ class MambaDirsFn(torch.autograd.Function):
         K = cw.shape[2]
         grads = ([d_cw[k].view(Dn, 1, K) for k in range(nd)]
                  + [d_cb[k] if ctx.has_conv_b else None for k in range(nd)]
-                 + [d_xw[k, :R2] for k in range(nd)] + [d_dw[k] for k in range(nd)]
+                 + [d_xw[k] for k in range(nd)] + [d_dw[k, :, :R] for k in range(nd)]
                  + [dA[k * Dn:(k + 1) * Dn] for k in range(nd)] + [dD[k * Dn:(k + 1) * Dn] for k in range(nd)]
                  + [ddt_b[k * Dn:(k + 1) * Dn] for k in range(nd)])
         return (d_hidden, d_in_w, d_in_b, d_out_w, d_out_b, None, None, None, None, *grads)
