@@ -21,6 +21,9 @@ batch = 4 if infer else 3
 clip = torch.randn(batch, 5, 3, 256, 256, device=dev)
 target = torch.randint(0, 3, (batch * 5, 256, 256), device=dev)
 loss_fn = RecallFocusedLoss().to(dev)
+if "--torch-layernorm" not in sys.argv:     # what bench.py does: the SegFormer stages' nn.LayerNorm on the same kernels
+    from vivim_b200.layernorm import use_token_layernorm
+    use_token_layernorm(model)
 if infer:
     model.eval()
 else:
