@@ -33,6 +33,8 @@ CONV_CASES = [
     (2, 4, 2, 24, 2, V3),            # width 2, taps wrap over two pixels (nf = 2 < K - 1)
     (1, 4, 1, 40, 4, ("frames",)),   # degenerate: one frame, frames == fwd
     (1, 16, 5, 4096, 4, V3),         # Vivim stage 1 (a slice of the channels)
+    (1, 4, 8, 96, 4, V3),            # clip_length 8 (BASELINE configs[4])
+    (2, 3, 16, 40, 4, V3),           # the most frames the kernels stage (pixel tiles shrink to fit shared memory)
 ]
 
 
@@ -126,6 +128,10 @@ SCAN_CASES = [
     (2, 16, 1, 512, 16, ("fwd", "rev")),
     (1, 4, 5, 40, 3, ("frames",)),
     (1, 16, 5, 1024, 16, V3),        # Vivim stage 2 (a slice of the channels)
+    (1, 20, 8, 576, 16, V3),         # clip_length 8 (BASELINE configs[4]): the 8-frame instantiation of the run-wise gathers
+    (2, 8, 7, 64, 16, V3),           # 7 frames: the same instantiation with its last frame slot empty
+    (1, 8, 6, 104, 8, ("frames", "frames")),
+    (1, 8, 12, 64, 16, V3),          # more frames than the run-wise gathers serve: element-wise route
 ]
 
 

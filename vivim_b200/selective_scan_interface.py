@@ -171,33 +171,56 @@ def selective_scan_ref(u, delta, A, B, C, D=None, z=None, delta_bias=None, delta
 # fused inner block: conv1d+SiLU -> x_proj -> dt_proj -> selective scan (gated by z) [-> out_proj]
 # ---------------------------------------------------------------------------------------------
 
-def _project(conv_out, x_proj_weight, delta_proj_weight, A, B, C, B_proj_bias, C_proj_bias):
-    """x_dbl, delta, B, C from the conv output (reference: selective_scan_interface.py:181-210)."""
-    batch, _, L = conv_out.shape
-    rank = delta_proj_weight.shape[1]
-    dstate = A.shape[-1]
-    x_dbl = F.linear(conv_out.transpose(1, 2).reshape(batch * L, -1), x_proj_weight)   # (b l, R+2N)
-    delta = (delta_proj_weight @ x_dbl[:, :rank].t()).view(-1, batch, L).transpose(0, 1)  # (b, d, l) view
+def _xdbl_layout(rank, dstate):
+    """Column layout of x_dbl inside the fused inner functions: [dt (rank) | zeros | B (dstate) | C (dstate) | zeros] with the
+    dt block and the whole row padded to multiples of 8 elements.  The reference packs rank + 2*dstate columns (36 at
+    Vivim's stage 1), which leaves every GEMM that touches x_dbl / dx_dbl on 4-byte aligned operands (cuBLAS then picks its
+    slow `align2` kernels: 370 us of a 1.15 ms block, profiles/r02_block.md).  -> (Rp, R2p): offset of B, padded width."""
+    Rp = -(-rank // 8) * 8
+    return Rp, -(-(Rp + 2 * dstate) // 8) * 8
 
-    def pick(M, lo, hi, proj_bias, name):
+
+def _pad_proj_weights(x_proj_weight, delta_proj_weight, dstate):
+    """x_proj (rank+2N, d) -> (R2p, d), dt_proj (d, rank) -> (d, Rp): zero rows / columns in the padding."""
+    rank = delta_proj_weight.shape[1]
+    Rp, R2p = _xdbl_layout(rank, dstate)
+    if Rp == rank and R2p == rank + 2 * dstate:
+        return x_proj_weight, delta_proj_weight
+    xw = x_proj_weight.new_zeros(R2p, x_proj_weight.shape[1])
+    xw[:rank] = x_proj_weight[:rank]
+    xw[Rp:Rp + 2 * dstate] = x_proj_weight[rank:]
+    dw = delta_proj_weight.new_zeros(delta_proj_weight.shape[0], Rp)
+    dw[:, :rank] = delta_proj_weight
+    return xw, dw
+
+
+def _project(conv_out, xw, dw, rank, A, B, C, B_proj_bias, C_proj_bias):
+    """x_dbl, delta, B, C from the conv output (reference: selective_scan_interface.py:181-210); xw / dw are the padded
+    projection weights of _pad_proj_weights."""
+    batch, _, L = conv_out.shape
+    dstate = A.shape[-1]
+    Rp = dw.shape[1]
+    x_dbl = F.linear(conv_out.transpose(1, 2).reshape(batch * L, -1), xw)              # (b l, R2p)
+    delta = _delta_from(x_dbl, dw, batch, L)                                           # (b, d, l) view
+
+    def pick(M, lo, proj_bias, name):
         if M is not None:   # caller-provided B / C: not input-dependent through x_proj
             return _as_groups(M, conv_out, A, name)
-        cols = x_dbl[:, lo:hi]
+        cols = x_dbl[:, lo:lo + dstate]
         if proj_bias is not None:
             cols = (cols + proj_bias.to(cols.dtype)).reshape(batch, L, dstate).transpose(1, 2).contiguous().unsqueeze(1)
             return cols, "proj"
-        # No copy: a (b, 1, n, l) VIEW of x_dbl's columns (state stride 1, sequence stride R+2N) -- the kernels read B / C
+        # No copy: a (b, 1, n, l) VIEW of x_dbl's columns (state stride 1, sequence stride R2p) -- the kernels read B / C
         # from the rows of the GEMM output where the reference transposes them (selective_scan_interface.py:187-207)
         return cols.unflatten(0, (batch, L)).permute(0, 2, 1).unsqueeze(1), "proj"
 
-    Bm, kind_B = pick(B, rank, rank + dstate, B_proj_bias, "B")
-    Cm, kind_C = pick(C, x_dbl.shape[1] - dstate, x_dbl.shape[1], C_proj_bias, "C")
+    Bm, kind_B = pick(B, Rp, B_proj_bias, "B")
+    Cm, kind_C = pick(C, Rp + dstate, C_proj_bias, "C")
     return x_dbl, delta, Bm, Cm, kind_B, kind_C
 
 
-def _delta_from(x_dbl, delta_proj_weight, batch, L):
-    rank = delta_proj_weight.shape[1]
-    return (delta_proj_weight @ x_dbl[:, :rank].t()).view(-1, batch, L).transpose(0, 1)
+def _delta_from(x_dbl, dw, batch, L):
+    return (dw @ x_dbl[:, :dw.shape[1]].t()).view(-1, batch, L).transpose(0, 1)
 
 
 class _MambaInner(torch.autograd.Function):
@@ -225,8 +248,9 @@ class _MambaInner(torch.autograd.Function):
         conv_b = conv1d_bias.contiguous() if conv1d_bias is not None else None
         x, z = xz.chunk(2, dim=1)                              # views: batch stride 2*D*L
         conv_out = causal_conv1d_cuda.causal_conv1d_fwd(x, conv_w, conv_b, True)
-        x_dbl, delta, Bm, Cm, kind_B, kind_C = _project(
-            conv_out, x_proj_weight, delta_proj_weight, A, B, C, B_proj_bias, C_proj_bias)
+        rank = delta_proj_weight.shape[1]
+        xw, dw = _pad_proj_weights(x_proj_weight, delta_proj_weight, A.shape[-1])
+        x_dbl, delta, Bm, Cm, kind_B, kind_C = _project(conv_out, xw, dw, rank, A, B, C, B_proj_bias, C_proj_bias)
         if D is not None:
             D = D.contiguous()
         _, chk, _, out_z = selective_scan_cuda.fwd(
@@ -237,7 +261,8 @@ class _MambaInner(torch.autograd.Function):
         ctx.has_B_bias, ctx.has_C_bias = B_proj_bias is not None, C_proj_bias is not None
         ctx.has_out_bias = out_proj_bias is not None
         ctx.recompute = checkpoint_lvl >= 1
-        ctx.save_for_backward(xz, conv_w, conv_b, x_dbl, x_proj_weight, delta_proj_weight,
+        ctx.rank = rank
+        ctx.save_for_backward(xz, conv_w, conv_b, x_dbl, xw, dw,
                               out_proj_weight if has_out_proj else None,
                               None if ctx.recompute else conv_out, None if ctx.recompute else delta,
                               A, Bm, Cm, D, delta_bias, chk, out_z if has_out_proj else None)
@@ -248,16 +273,17 @@ class _MambaInner(torch.autograd.Function):
     @staticmethod
     @_bwd_amp
     def backward(ctx, dout):
-        (xz, conv_w, conv_b, x_dbl, x_proj_weight, delta_proj_weight, out_proj_weight,
+        (xz, conv_w, conv_b, x_dbl, xw, dw, out_proj_weight,
          conv_out, delta, A, Bm, Cm, D, delta_bias, chk, out_z) = ctx.saved_tensors
         batch, two_d, L = xz.shape
         dim = two_d // 2
-        rank = delta_proj_weight.shape[1]
+        rank, Rp = ctx.rank, dw.shape[1]          # x_dbl columns: [dt (rank) | 0 | B | C | 0], see _xdbl_layout
         dstate = A.shape[-1]
+        cB, cC, cEnd = Rp, Rp + dstate, Rp + 2 * dstate
         x, z = xz.chunk(2, dim=1)
         if ctx.recompute:
             conv_out = causal_conv1d_cuda.causal_conv1d_fwd(x, conv_w, conv_b, True)
-            delta = _delta_from(x_dbl, delta_proj_weight, batch, L)
+            delta = _delta_from(x_dbl, dw, batch, L)
         dout_proj_weight = dout_proj_bias = None
         if ctx.has_out_proj:
             dflat = dout.reshape(batch * L, -1)                                      # (b l, e)
@@ -270,43 +296,45 @@ class _MambaInner(torch.autograd.Function):
         dxz = torch.empty_like(xz)
         dx, dz = dxz.chunk(2, dim=1)
         dx_dbl = torch.empty_like(x_dbl)
+        if dx_dbl.shape[1] != cEnd:
+            dx_dbl[:, cEnd:] = 0                   # trailing padding; the dt padding is written (as zeros) by the GEMM below
         both_proj = ctx.kind_B == "proj" and ctx.kind_C == "proj"
         dBC_out = None
         if both_proj:
             # dB / dC land straight in their column blocks of dx_dbl (the cast kernel of vv_scan_bwd writes them there):
             # no rearrange + slice copy (selective_scan_interface.py:255-271)
             cols = lambda lo, hi: dx_dbl[:, lo:hi].unflatten(0, (batch, L)).permute(0, 2, 1).unsqueeze(1)  # noqa: E731
-            dBC_out = (cols(rank, rank + dstate), cols(x_dbl.shape[1] - dstate, x_dbl.shape[1]))
+            dBC_out = (cols(cB, cC), cols(cC, cEnd))
         dconv, ddelta, dA, dB, dC, dD, ddelta_bias, dz = selective_scan_cuda.bwd(
             conv_out, delta, A, Bm, Cm, D, z, delta_bias, dout_y, chk, dz, ctx.delta_softplus, dBC_out=dBC_out)
         dB_out = dC_out = dB_proj_bias = dC_proj_bias = None
         if both_proj:
-            dB_proj_bias = dx_dbl[:, rank:rank + dstate].sum(0) if ctx.has_B_bias else None
-            dC_proj_bias = dx_dbl[:, -dstate:].sum(0) if ctx.has_C_bias else None
+            dB_proj_bias = dx_dbl[:, cB:cC].sum(0) if ctx.has_B_bias else None
+            dC_proj_bias = dx_dbl[:, cC:cEnd].sum(0) if ctx.has_C_bias else None
         else:
             if ctx.kind_B == "proj":
                 dBf = dB.squeeze(1).transpose(1, 2).reshape(batch * L, dstate)
                 dB_proj_bias = dBf.sum(0) if ctx.has_B_bias else None
-                dx_dbl[:, rank:rank + dstate] = dBf
+                dx_dbl[:, cB:cC] = dBf
             else:
                 dB_out = _ungroup_grad(dB, ctx.kind_B)
-                dx_dbl[:, rank:rank + dstate] = 0
+                dx_dbl[:, cB:cC] = 0
             if ctx.kind_C == "proj":
                 dCf = dC.squeeze(1).transpose(1, 2).reshape(batch * L, dstate)
                 dC_proj_bias = dCf.sum(0) if ctx.has_C_bias else None
-                dx_dbl[:, -dstate:] = dCf
+                dx_dbl[:, cC:cEnd] = dCf
             else:
                 dC_out = _ungroup_grad(dC, ctx.kind_C)
-                dx_dbl[:, -dstate:] = 0
+                dx_dbl[:, cC:cEnd] = 0
         ddelta_f = ddelta.transpose(0, 1).reshape(dim, batch * L)                     # (d, b l)
-        ddelta_proj_weight = ddelta_f @ x_dbl[:, :rank]
-        dx_dbl[:, :rank] = ddelta_f.t() @ delta_proj_weight
+        ddelta_proj_weight = (ddelta_f @ x_dbl[:, :Rp])[:, :rank]
+        dx_dbl[:, :Rp] = ddelta_f.t() @ dw                                            # zeros beyond `rank`
         conv_flat = conv_out.transpose(1, 2).reshape(batch * L, dim)                  # (b l, d)
-        dx_proj_weight = dx_dbl.t() @ conv_flat
-        # dconv (b, d, l) += x_proj_weight^T (d, R+2N) @ dx_dbl^T (R+2N, l), per batch entry, accumulated in place in the
+        dxw = dx_dbl.t() @ conv_flat                                                  # (R2p, d)
+        dx_proj_weight = dxw if cEnd == rank + 2 * dstate and Rp == rank else torch.cat([dxw[:rank], dxw[cB:cEnd]])
+        # dconv (b, d, l) += x_proj_weight^T (d, R2p) @ dx_dbl^T (R2p, l), per batch entry, accumulated in place in the
         # kernels' (b, d, l) layout (no (b, l, d) intermediate and transposing add)
-        dconv.baddbmm_(x_proj_weight.t().unsqueeze(0).expand(batch, -1, -1),
-                       dx_dbl.view(batch, L, -1).transpose(1, 2))
+        dconv.baddbmm_(xw.t().unsqueeze(0).expand(batch, -1, -1), dx_dbl.view(batch, L, -1).transpose(1, 2))
         dx, dconv_w, dconv_b = causal_conv1d_cuda.causal_conv1d_bwd(x, conv_w, conv_b, dconv, dx, True)
         return (dxz, dconv_w.unsqueeze(1), dconv_b, dx_proj_weight, ddelta_proj_weight,
                 dout_proj_weight, dout_proj_bias, dA, dB_out, dC_out, dD, ddelta_bias,
@@ -337,7 +365,8 @@ def _inner_pre(xz, conv1d_weight, conv1d_bias, x_proj_weight, delta_proj_weight,
                B_proj_bias, C_proj_bias, conv_fn):
     x, z = xz.chunk(2, dim=1)
     xc = conv_fn(x, conv1d_weight.squeeze(1), conv1d_bias, "silu")
-    _, delta, Bm, Cm, _, _ = _project(xc, x_proj_weight, delta_proj_weight, A, B, C, B_proj_bias, C_proj_bias)
+    xw, dw = _pad_proj_weights(x_proj_weight, delta_proj_weight, A.shape[-1])
+    _, delta, Bm, Cm, _, _ = _project(xc, xw, dw, delta_proj_weight.shape[1], A, B, C, B_proj_bias, C_proj_bias)
     return xc, z, delta, Bm, Cm
 
 
