@@ -11,8 +11,9 @@
 //     forward   reads T bytes, writes ndirs * T          (the reference: ndirs * 2T plus 4T of flip / interleave copies)
 //     backward  reads (1 + ndirs) * T, writes T          (the reference: ndirs * 3T plus the copies and the dx sums)
 // Layout of the work: x is (B, D, L) with L = nf * HW tokens (frame, pixel); a CTA owns (row, pixels [p0, p0 + pt)) for
-// all nf frames; thread i of the CTA owns pixels p0 + i, p0 + i + 128, ...: consecutive threads read consecutive
-// shared-memory words (no bank conflicts) and write consecutive global elements.
+// all nf frames (pt = 512, or 1024 without a frame-interleaved direction).  128-bit route (HW % 8 == 0): a thread owns 4
+// consecutive pixels of a frame -- 128-bit shared loads at 16-byte stride (conflict-free), 64-bit global stores; the
+// element-wise route (ragged HW) owns single pixels, consecutive threads on consecutive pixels.
 //   FWD     out[m] = bias + sum_i w[i] x[m - 3 + i]                      taps to the left in memory
 //   REV     out[m] = bias + sum_i w[i] x[m + 3 - i]                      taps to the right
 //   FRAMES  token (t, p) is position j = p nf + t of the traversal; tap j - k lives at frame t - k of the same pixel,

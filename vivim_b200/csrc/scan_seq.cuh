@@ -29,7 +29,11 @@
 //     peak (bench.py "mufu_roofline").  The forward kernel (35 KB: B and C tiles plus the output staging) is bound
 //     by shared-memory wavefronts instead, 11.75 per warp and position against 6 in the aggregate kernels.
 //   * launched as programmatic dependents: a kernel's loads, pre-pass and tile fills overlap the tail of its
-//     predecessor; its first access to what the predecessor wrote (or may still read) comes after the wait.
+//     predecessor; its first access to what the predecessor wrote (or may still read) comes after the wait.  The FIRST
+//     kernel of a call (seg_agg_kernel) is the exception: its predecessor is the caller's, so it waits before it reads
+//     anything and only prefetches to L2 ahead of the wait.
+//   * direction blocks (kGen = true): every load / store goes through a traversal order (Trav); B / C may be rows of
+//     x_proj's output; z and the upstream gradient may be shared by the blocks.  kGen = false folds all of it away.
 //
 //   pass 1  seg_agg_kernel    (P, X) of every (row, segment, state), forward or reverse
 //   pass 2  seg_carry_kernel  per row: fold the segment aggregates -> state entering each segment
