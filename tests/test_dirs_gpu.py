@@ -264,3 +264,38 @@ def test_fused_block_launch_count(cuda_device):
             pytest.skip(f"torch profiler unavailable: {e}")
     print(f"[launches per Mamba(v3) fwd+bwd] fused {counts[True]}  three-call {counts[False]}")
     assert 0 < counts[True] < counts[False]
+
+
+@pytest.mark.parametrize("shared_gate", [True, False])
+def test_selective_scan_dirs_fn_autograd(cuda_device, shared_gate):
+    """The public multi-direction op (selective_scan_dirs_fn) through autograd == one selective_scan_fn per direction on
+    gathered copies, summed gradients for the shared gate."""
+    from mamba_ssm.ops.selective_scan_interface import selective_scan_fn
+    from vivim_b200.selective_scan_interface import selective_scan_dirs_fn
+    torch.manual_seed(1)
+    B_, D, nf, hw, N = 2, 16, 5, 64, 16
+    L = nf * hw
+    mk = lambda *s: torch.randn(*s, device="cuda").requires_grad_()  # noqa: E731
+    u, delta = mk(B_, 3 * D, L), (0.5 * torch.rand(B_, 3 * D, L, device="cuda")).requires_grad_()
+    A = (-0.5 * torch.rand(3 * D, N, device="cuda")).requires_grad_()
+    Bm, Cm = mk(B_, 3, N, L), mk(B_, 3, N, L)
+    Dv, bias = mk(3 * D), (0.5 * torch.rand(3 * D, device="cuda")).requires_grad_()
+    z = mk(B_, D if shared_gate else 3 * D, L)
+    g = torch.randn(B_, 3 * D, L, device="cuda")
+    leaves = (u, delta, A, Bm, Cm, Dv, z, bias)
+    out = selective_scan_dirs_fn(u, delta, A, Bm, Cm, Dv, z=z, delta_bias=bias, delta_softplus=True, dirs=V3, nframes=nf)
+    got = [host(out)] + [host(t) for t in torch.autograd.grad(out, leaves, g)]
+    outs = []
+    for k, mode in enumerate(V3):
+        p = _perm(mode, L, nf)
+        ch = slice(k * D, (k + 1) * D)
+        zk = (z if shared_gate else z[:, ch])[:, :, p]
+        o = selective_scan_fn(u[:, ch][:, :, p], delta[:, ch][:, :, p], A[ch], Bm[:, k][:, :, p], Cm[:, k][:, :, p], Dv[ch],
+                              z=zk, delta_bias=bias[ch], delta_softplus=True)
+        full = torch.zeros(B_, D, L, device="cuda")
+        full[:, :, p] = o
+        outs.append(full)
+    ref = torch.cat(outs, dim=1)
+    want = [host(ref)] + [host(t) for t in torch.autograd.grad(ref, leaves, g)]
+    for name, a, b in zip(("out", "du", "ddelta", "dA", "dB", "dC", "dD", "dz", "dbias"), got, want):
+        assert rel_err(a, b) < 1e-4, (name, rel_err(a, b))
