@@ -4,6 +4,9 @@ test body runs (outputs, gradients, the checkpoint / aggregate / carry scratch) 
 must still hold it.  The bodies are the ragged cases of the other GPU tests: sequence lengths around the 64-position
 segment, channel counts that leave warps and channel groups partly empty, frame counts on both gather routes.
 
+`torch.empty` bodies are filled with 0xFF bytes (NaN in every floating type), so reliance on memory that happens to
+be zero shows up as NaN in the body's own comparison with the oracle.
+
 A write further than 8 KiB away is not seen; a read out of bounds is not seen either (those show up as wrong values
 in the parity comparisons only if the data matters) -- this is a tripwire, not a proof."""
 import contextlib
@@ -37,6 +40,9 @@ class GuardBands:
         body = raw[BAND:BAND + nbytes].view(dtype).view(tuple(shape))
         if zero:
             body.zero_()
+        else:
+            raw[BAND:BAND + nbytes].fill_(0xFF)      # NaN in fp32 / bf16 / fp16: a kernel that reads (or accumulates into)
+                                                     # memory nobody initialised fails the body's parity comparison
         self.allocs.append((raw, nbytes))
         return body
 
