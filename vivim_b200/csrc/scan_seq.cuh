@@ -77,6 +77,28 @@ __device__ __forceinline__ void load_states(const float* __restrict__ p, float (
     }
 }
 
+// the same NQ states as NQ / 2 register pairs, the operands of the packed fp32x2 instructions (FMUL2 / FFMA2)
+template <int NQ>
+__device__ __forceinline__ void load_state_pairs(const float* __restrict__ p, float2 (&v)[NQ / 2]) {
+    static_assert(NQ % 2 == 0, "states per lane come in pairs");
+    if (NQ % 4 == 0) {
+#pragma unroll
+        for (int k = 0; k < NQ / 4; ++k) {
+            const float4 x = reinterpret_cast<const float4*>(p)[k];
+            v[2 * k] = make_float2(x.x, x.y);
+            v[2 * k + 1] = make_float2(x.z, x.w);
+        }
+    } else {
+        v[0] = *reinterpret_cast<const float2*>(p);
+    }
+}
+
+// decays of a state pair: exp2(dt * A * log2 e)
+__device__ __forceinline__ float2 decay2(float2 dt2, float2 A2) {
+    const float2 x = mul2(dt2, A2);
+    return make_float2(exp2f(x.x), exp2f(x.y));
+}
+
 // Four consecutive states of one token, from any (state stride, sequence stride) layout: the (B,G,N,L) tensors of the
 // reference op (ns = L, ls = 1) or rows of x_proj's GEMM output x_dbl (ns = 1, ls = R+2N; reference:
 // selective_scan_interface.py:187-207 transposes those into (B,1,N,L) first).  Kept packed until store time.
@@ -361,12 +383,15 @@ __global__ void __launch_bounds__(kSegThreads, (kVec && NB <= 16 && sizeof(T) ==
                  a.z ? reinterpret_cast<const T*>(a.z) + c.b * a.z_bs + dg * a.z_ds : nullptr, live, q, c.t0, c.tr, s_dt, s_cf, s_z);
         st.load(reinterpret_cast<const T*>(a.Cm) + c.b * a.C_bs + c.g * a.C_gs, a.C_ns, a.C_ls, N, c.t0, c.tr, kGen);
     }
-    float A2[NQ], h[NQ];
+    // two states per register pair: the recurrences run on the packed fp32x2 pipe (same roundings as the scalar form)
+    constexpr int NP = NQ / 2;
+    float2 A2[NP], h[NP];
 #pragma unroll
-    for (int k = 0; k < NQ; ++k) {
-        const int n = q * NQ + k;
-        A2[k] = n < N ? a.A[d * a.A_ds + n * a.A_ns] * kLog2e : 0.f;
-        h[k] = 0.f;
+    for (int k = 0; k < NP; ++k) {
+        const int n = q * NQ + 2 * k;
+        A2[k].x = n < N ? a.A[d * a.A_ds + n * a.A_ns] * kLog2e : 0.f;
+        A2[k].y = n + 1 < N ? a.A[d * a.A_ds + (n + 1) * a.A_ns] * kLog2e : 0.f;
+        h[k] = make_float2(0.f, 0.f);
     }
     float sum_dt = 0.f;
     st.store(t_m);
@@ -386,15 +411,16 @@ __global__ void __launch_bounds__(kSegThreads, (kVec && NB <= 16 && sizeof(T) ==
             const int i = kRev ? 3 - ii : ii;
             const float dti = dts[i];
             sum_dt += dti;
-            float m[NQ];
-            load_states<NQ>(t_m + (j * 4 + i) * NB + q * NQ, m);
+            const float2 dt2 = make_float2(dti, dti), cf2 = make_float2(cfs[i], cfs[i]);
+            float2 m[NP];
+            load_state_pairs<NQ>(t_m + (j * 4 + i) * NB + q * NQ, m);
             if (!kRev) {
 #pragma unroll
-                for (int k = 0; k < NQ; ++k) h[k] = fmaf(exp2f(dti * A2[k]), h[k], cfs[i] * m[k]);
+                for (int k = 0; k < NP; ++k) h[k] = fma2(decay2(dt2, A2[k]), h[k], mul2(cf2, m[k]));
             } else {
                 // pushed adjoint e_t = a_t r_t:  e_t = a_t (e_{t+1} + g_t C_t)
 #pragma unroll
-                for (int k = 0; k < NQ; ++k) h[k] = exp2f(dti * A2[k]) * fmaf(cfs[i], m[k], h[k]);
+                for (int k = 0; k < NP; ++k) h[k] = mul2(decay2(dt2, A2[k]), fma2(cf2, m[k], h[k]));
             }
         }
     }
@@ -426,9 +452,10 @@ __global__ void __launch_bounds__(kSegThreads, (kVec && NB <= 16 && sizeof(T) ==
         }
     }
 #pragma unroll
-    for (int k = 0; k < NQ; ++k) {
-        const int n = q * NQ + k;
-        if (n < N) out[n] = make_float2(exp2f(A2[k] * sum_dt), h[k]);
+    for (int k = 0; k < NP; ++k) {
+        const int n = q * NQ + 2 * k;
+        if (n < N) out[n] = make_float2(exp2f(A2[k].x * sum_dt), h[k].x);
+        if (n + 1 < N) out[n + 1] = make_float2(exp2f(A2[k].y * sum_dt), h[k].y);
     }
 }
 
@@ -540,11 +567,13 @@ __global__ void __launch_bounds__(kSegThreads, (kVec && NB <= 16) ? 7 : 4) seg_f
              reinterpret_cast<T*>(t_z + r * SegTile<T>::kPitch));
     stB.load(reinterpret_cast<const T*>(a.Bm) + c.b * a.B_bs + c.g * a.B_gs, a.B_ns, a.B_ls, N, c.t0, c.tr, kGen);
     stC.load(reinterpret_cast<const T*>(a.Cm) + c.b * a.C_bs + c.g * a.C_gs, a.C_ns, a.C_ls, N, c.t0, c.tr, kGen);
-    float A2[NQ], h[NQ];
+    constexpr int NP = NQ / 2;   // state pairs: packed fp32x2 recurrences, as in seg_agg_kernel
+    float2 A2[NP], h[NP];
 #pragma unroll
-    for (int k = 0; k < NQ; ++k) {
-        const int n = q * NQ + k;
-        A2[k] = n < N ? a.A[d * a.A_ds + n * a.A_ns] * kLog2e : 0.f;
+    for (int k = 0; k < NP; ++k) {
+        const int n = q * NQ + 2 * k;
+        A2[k].x = n < N ? a.A[d * a.A_ds + n * a.A_ns] * kLog2e : 0.f;
+        A2[k].y = n + 1 < N ? a.A[d * a.A_ds + (n + 1) * a.A_ns] * kLog2e : 0.f;
     }
     pdl_trigger();   // a dependent launch (the reverse aggregate of a backward that follows directly) may start its loads
     stB.store(t_B);
@@ -555,9 +584,10 @@ __global__ void __launch_bounds__(kSegThreads, (kVec && NB <= 16) ? 7 : 4) seg_f
     {
         const float* E = a.chk + (((int64_t)c.b * a.dim + d) * S + c.seg) * N;
 #pragma unroll
-        for (int k = 0; k < NQ; ++k) {
-            const int n = q * NQ + k;
-            h[k] = n < N ? E[n] : 0.f;
+        for (int k = 0; k < NP; ++k) {
+            const int n = q * NQ + 2 * k;
+            h[k].x = n < N ? E[n] : 0.f;
+            h[k].y = n + 1 < N ? E[n + 1] : 0.f;
         }
     }
     __syncthreads();
@@ -590,16 +620,17 @@ __global__ void __launch_bounds__(kSegThreads, (kVec && NB <= 16) ? 7 : 4) seg_f
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
                     const int t = ch * 8 + half * 4 + i;
-                    float bm[NQ], cm[NQ];
-                    load_states<NQ>(t_B + t * NB + q * NQ, bm);
-                    load_states<NQ>(t_C + t * NB + q * NQ, cm);
-                    float acc = 0.f;
+                    const float2 dt2 = make_float2(dts[i], dts[i]), dr2 = make_float2(drs[i], drs[i]);
+                    float2 bm[NP], cm[NP];
+                    load_state_pairs<NQ>(t_B + t * NB + q * NQ, bm);
+                    load_state_pairs<NQ>(t_C + t * NB + q * NQ, cm);
+                    float2 acc = make_float2(0.f, 0.f);   // even / odd states; the 4 lanes of the channel are summed below
 #pragma unroll
-                    for (int k = 0; k < NQ; ++k) {
-                        h[k] = fmaf(exp2f(dts[i] * A2[k]), h[k], drs[i] * bm[k]);
-                        acc = fmaf(cm[k], h[k], acc);
+                    for (int k = 0; k < NP; ++k) {
+                        h[k] = fma2(decay2(dt2, A2[k]), h[k], mul2(dr2, bm[k]));
+                        acc = fma2(cm[k], h[k], acc);
                     }
-                    y[half * 4 + i] = acc;
+                    y[half * 4 + i] = acc.x + acc.y;
                 }
             }
             // reduce-scatter of the 8 partial sums over the 4 lanes of the channel: lane q ends with {2q, 2q+1}
