@@ -357,6 +357,7 @@ __global__ void __launch_bounds__(kSegThreads, (kVec && NB <= 16 && sizeof(T) ==
                               : reinterpret_cast<const T*>(a.u) + c.b * a.u_bs + d * a.u_ds;
 #pragma unroll
         for (int h = 0; h < (int)sizeof(T) / 2; ++h) {
+            if (m0 + h * (kSeg / 2) >= L) break;   // never form an address past the row
             prefetch_l2(g_dt + m0 + h * (kSeg / 2));
             prefetch_l2(g_cf0 + m0 + h * (kSeg / 2));
             if (kRev && a.z) prefetch_l2(reinterpret_cast<const T*>(a.z) + c.b * a.z_bs + dg * a.z_ds + m0 + h * (kSeg / 2));
@@ -364,6 +365,28 @@ __global__ void __launch_bounds__(kSegThreads, (kVec && NB <= 16 && sizeof(T) ==
     }
     pdl_wait();
     pdl_trigger();
+    // Rows that only the MAIN kernel of this pass reads -- z and C in the forward, u and B in the backward -- start their
+    // way to L2 now (hints): that kernel's CTAs all start at once and would otherwise wait for HBM together.
+    if (c.tr.mode != VV_DIR_FRAMES && c.t0 < L) {
+        const int m0 = c.tr.mode == VV_DIR_REV ? max(L - kSeg - c.t0, 0) : c.t0;
+        if (live && q == 1) {
+            const T* row = kRev ? reinterpret_cast<const T*>(a.u) + c.b * a.u_bs + d * a.u_ds
+                                : (a.z ? reinterpret_cast<const T*>(a.z) + c.b * a.z_bs + dg * a.z_ds : nullptr);
+            if (row != nullptr) {
+#pragma unroll
+                for (int h = 0; h < (int)sizeof(T) / 2; ++h)
+                    if (m0 + h * (kSeg / 2) < L) prefetch_l2(row + m0 + h * (kSeg / 2));
+            }
+        }
+        const int64_t o_ls = kRev ? a.B_ls : a.C_ls;
+        if (q == 2 && r < N && o_ls <= 1 && c.d0 == c.g * (a.dim / a.ngroups)) {   // state-major rows, once per group
+            const T* row = kRev ? reinterpret_cast<const T*>(a.Bm) + c.b * a.B_bs + c.g * a.B_gs + r * a.B_ns
+                                : reinterpret_cast<const T*>(a.Cm) + c.b * a.C_bs + c.g * a.C_gs + r * a.C_ns;
+#pragma unroll
+            for (int h = 0; h < (int)sizeof(T) / 2; ++h)
+                if (m0 + h * (kSeg / 2) < L) prefetch_l2(row + m0 + h * (kSeg / 2));
+        }
+    }
 
     const float bias = a.delta_bias ? a.delta_bias[d] : 0.f;
     const bool sp = a.delta_softplus != 0;
