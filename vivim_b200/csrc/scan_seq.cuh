@@ -379,12 +379,21 @@ __global__ void __launch_bounds__(kSegThreads, (kVec && NB <= 16 && sizeof(T) ==
             }
         }
         const int64_t o_ls = kRev ? a.B_ls : a.C_ls;
-        if (q == 2 && r < N && o_ls <= 1 && c.d0 == c.g * (a.dim / a.ngroups)) {   // state-major rows, once per group
-            const T* row = kRev ? reinterpret_cast<const T*>(a.Bm) + c.b * a.B_bs + c.g * a.B_gs + r * a.B_ns
-                                : reinterpret_cast<const T*>(a.Cm) + c.b * a.C_bs + c.g * a.C_gs + r * a.C_ns;
+        if (c.d0 == c.g * (a.dim / a.ngroups)) {   // B / C of the other kind, once per group
+            const T* base = kRev ? reinterpret_cast<const T*>(a.Bm) + c.b * a.B_bs + c.g * a.B_gs
+                                 : reinterpret_cast<const T*>(a.Cm) + c.b * a.C_bs + c.g * a.C_gs;
+            if (o_ls <= 1) {                       // state-major rows
+                if (q == 2 && r < N) {
+                    const T* row = base + r * (kRev ? a.B_ns : a.C_ns);
 #pragma unroll
-            for (int h = 0; h < (int)sizeof(T) / 2; ++h)
-                if (m0 + h * (kSeg / 2) < L) prefetch_l2(row + m0 + h * (kSeg / 2));
+                    for (int h = 0; h < (int)sizeof(T) / 2; ++h)
+                        if (m0 + h * (kSeg / 2) < L) prefetch_l2(row + m0 + h * (kSeg / 2));
+                }
+            } else if (kGen) {                     // position-major: the segment's rows of x_dbl are one contiguous span
+                const char* p0 = reinterpret_cast<const char*>(base + (int64_t)m0 * o_ls);
+                const int64_t bytes = ((int64_t)(min(kSeg, L - m0) - 1) * o_ls + N) * (int64_t)sizeof(T);
+                for (int64_t off = (int64_t)threadIdx.x * 128; off < bytes; off += 128 * kSegThreads) prefetch_l2(p0 + off);
+            }
         }
     }
 
