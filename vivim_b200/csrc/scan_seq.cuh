@@ -321,6 +321,24 @@ struct SegPrepass {
     }
 };
 
+// L2 hints for the B or C values of one segment (memory positions [m0, m0 + kSeg)): state-major rows -- thread `id` < N
+// takes state row `id` -- or, position-major, the contiguous span of the segment's x_dbl rows, 128 bytes per thread.
+template <typename T>
+__device__ __forceinline__ void prefetch_state_tile(const T* __restrict__ base, int64_t ns, int64_t ls, int N, int m0, int L,
+                                                    int id, int nthreads) {
+    if (ls <= 1) {
+        if (id < N) {
+#pragma unroll
+            for (int h = 0; h < (int)sizeof(T) / 2; ++h)
+                if (m0 + h * (kSeg / 2) < L) prefetch_l2(base + id * ns + m0 + h * (kSeg / 2));
+        }
+    } else {
+        const char* p0 = reinterpret_cast<const char*>(base + (int64_t)m0 * ls);
+        const int64_t bytes = ((int64_t)(min(kSeg, L - m0) - 1) * ls + N) * (int64_t)sizeof(T);
+        for (int64_t off = (int64_t)id * 128; off < bytes; off += 128 * nthreads) prefetch_l2(p0 + off);
+    }
+}
+
 // ================================================================ pass 1: segment aggregates
 // Lane (channel r, quad q) owns states [q*NQ, (q+1)*NQ) of channel r, NQ = NB/4.
 // smem: [f32 dt][f32 coef][state tile fp32]
@@ -363,6 +381,15 @@ __global__ void __launch_bounds__(kSegThreads, (kVec && NB <= 16 && sizeof(T) ==
             if (kRev && a.z) prefetch_l2(reinterpret_cast<const T*>(a.z) + c.b * a.z_bs + dg * a.z_ds + m0 + h * (kSeg / 2));
         }
     }
+    const bool first_block = c.d0 == c.g * (a.dim / a.ngroups);   // one CTA per (batch, group, segment) hints B / C
+    if (first_block && threadIdx.x >= kSegThreads / 2 && c.tr.mode != VV_DIR_FRAMES && c.t0 < L) {
+        // the state tile this kernel itself reads (B forward, C reverse), by the second half of the CTA
+        const int m0 = c.tr.mode == VV_DIR_REV ? max(L - kSeg - c.t0, 0) : c.t0;
+        const T* base = kRev ? reinterpret_cast<const T*>(a.Cm) + c.b * a.C_bs + c.g * a.C_gs
+                             : reinterpret_cast<const T*>(a.Bm) + c.b * a.B_bs + c.g * a.B_gs;
+        prefetch_state_tile<T>(base, kRev ? a.C_ns : a.B_ns, kGen ? (kRev ? a.C_ls : a.B_ls) : 1, N, m0, L,
+                               threadIdx.x - kSegThreads / 2, kSegThreads / 2);
+    }
     pdl_wait();
     pdl_trigger();
     // Rows that only the MAIN kernel of this pass reads -- z and C in the forward, u and B in the backward -- start their
@@ -378,22 +405,11 @@ __global__ void __launch_bounds__(kSegThreads, (kVec && NB <= 16 && sizeof(T) ==
                     if (m0 + h * (kSeg / 2) < L) prefetch_l2(row + m0 + h * (kSeg / 2));
             }
         }
-        const int64_t o_ls = kRev ? a.B_ls : a.C_ls;
-        if (c.d0 == c.g * (a.dim / a.ngroups)) {   // B / C of the other kind, once per group
+        if (first_block) {   // B / C of the other kind
             const T* base = kRev ? reinterpret_cast<const T*>(a.Bm) + c.b * a.B_bs + c.g * a.B_gs
                                  : reinterpret_cast<const T*>(a.Cm) + c.b * a.C_bs + c.g * a.C_gs;
-            if (o_ls <= 1) {                       // state-major rows
-                if (q == 2 && r < N) {
-                    const T* row = base + r * (kRev ? a.B_ns : a.C_ns);
-#pragma unroll
-                    for (int h = 0; h < (int)sizeof(T) / 2; ++h)
-                        if (m0 + h * (kSeg / 2) < L) prefetch_l2(row + m0 + h * (kSeg / 2));
-                }
-            } else if (kGen) {                     // position-major: the segment's rows of x_dbl are one contiguous span
-                const char* p0 = reinterpret_cast<const char*>(base + (int64_t)m0 * o_ls);
-                const int64_t bytes = ((int64_t)(min(kSeg, L - m0) - 1) * o_ls + N) * (int64_t)sizeof(T);
-                for (int64_t off = (int64_t)threadIdx.x * 128; off < bytes; off += 128 * kSegThreads) prefetch_l2(p0 + off);
-            }
+            prefetch_state_tile<T>(base, kRev ? a.B_ns : a.C_ns, kGen ? (kRev ? a.B_ls : a.C_ls) : 1, N, m0, L, threadIdx.x,
+                                   kSegThreads);
         }
     }
 
