@@ -134,7 +134,8 @@ class ClockSampler:
                     reasons.add(n)
         if not sm:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
-        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+        return {"sm_mhz": statistics.median(sm), "sm_min_mhz": min(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons),
+                "samples": len(sm)}
 
 
 
@@ -753,23 +754,27 @@ def bench_vivim(args, rank, world, device, torch, dist):
     warm = 3
 
     def timed(step_fn, batch):
-        for _ in range(warm):
-            step_fn()
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(steps):
-            out = step_fn()
-        e1.record()
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
+        # clocks of this leg too: it runs after a minute of scan benchmarks, on a warm GPU
+        with ClockSampler(device.index if device.index is not None else 0) as clk:
+            for _ in range(warm):
+                step_fn()
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize()
+            clk.wait_first_sample()
+            clk.mark()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(steps):
+                out = step_fn()
+            e1.record()
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize()
         t = torch.tensor([e0.elapsed_time(e1) / 1e3], device=device)
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return world * batch * steps / t.item(), t.item() / steps * 1e3, float(out)
+        return world * batch * steps / t.item(), t.item() / steps * 1e3, float(out), clk.summary()
 
     torch.manual_seed(0)
     model = Vivim(out_chans=3).to(device)
@@ -799,7 +804,7 @@ def bench_vivim(args, rank, world, device, torch, dist):
         opt.step()
         return loss
 
-    cps, ms, loss = timed(train_step, batch)
+    cps, ms, loss, clocks = timed(train_step, batch)
     res.update(vivim_train_clips_per_s=cps, vivim_train_ms_per_step=ms,
                vivim_train={"batch_per_gpu": batch, "steps": steps, "loss_after": loss, "loss": "recall_focused_loss",
                             "optimizer": "AdamW lr 1e-4 wd 1e-2 (fused)",
@@ -809,7 +814,8 @@ def bench_vivim(args, rank, world, device, torch, dist):
                                                 % (len(tsg._buckets), tsg.flat_grad.numel() * 4 / 1e6)) if overlapped else
                                                "one NCCL all_reduce(AVG) of the flat fp32 gradient (%.0f MB) after the graph replay"
                                                % (tsg.flat_grad.numel() * 4 / 1e6)),
-                            "launch": "forward + backward as one CUDA graph (vivim_b200.graphed.TrainStepGraph)"})
+                            "launch": "forward + backward as one CUDA graph (vivim_b200.graphed.TrainStepGraph)",
+                            "clocks": clocks})
     tsg.close()         # the graph holds NCCL nodes: release it before the process group is torn down
     del tsg, opt
     # ---- inference (configs[3]: 32 clips over 8 GPUs -> 4 per GPU)
@@ -817,9 +823,10 @@ def bench_vivim(args, rank, world, device, torch, dist):
     model.eval()
     clip = torch.randn(batch, frames, 3, image, image, device=device)
     infer = InferenceGraph(model, (clip,), autocast_dtype=torch.bfloat16)
-    cps, ms, _ = timed(lambda: infer().float().mean(), batch)
+    cps, ms, _, clocks = timed(lambda: infer().float().mean(), batch)
     res.update(vivim_infer_clips_per_s=cps, vivim_infer_ms_per_step=ms,
-               vivim_infer={"batch_per_gpu": batch, "steps": steps, "launch": "forward as one CUDA graph (InferenceGraph)"})
+               vivim_infer={"batch_per_gpu": batch, "steps": steps, "launch": "forward as one CUDA graph (InferenceGraph)",
+                            "clocks": clocks})
     res["vivim_config"] = {"workload": "Vivim multiclass, image 256, clip_length 5, 3 classes, random init, synthetic clips, bf16 autocast",
                            "layernorm": ("vivim_b200 TokenLayerNorm in the Temporal Mamba blocks and, re-classed in place, in %d SegFormer "
                                          "nn.LayerNorm modules" % n_ln) if n_ln else "vivim_b200 TokenLayerNorm in the Temporal Mamba blocks only",
