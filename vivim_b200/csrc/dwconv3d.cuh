@@ -211,7 +211,7 @@ __global__ void __launch_bounds__(kDwThreads, 2) dwconv3d_kernel(const T* __rest
 
 // weight / bias gradient: block (32 lanes = 64 channels, kDwCols columns), grid (ceil(C / 64), column blocks)
 template <typename T, bool kPair>
-__global__ void __launch_bounds__(32 * kDwCols) dwconv3d_wgrad_kernel(const T* __restrict__ x, const T* __restrict__ dout,
+__global__ void __launch_bounds__(32 * kDwCols, 2) dwconv3d_wgrad_kernel(const T* __restrict__ x, const T* __restrict__ dout,
                                                                       float* __restrict__ dweight, float* __restrict__ dbias,
                                                                       const DwGeom g) {
     __shared__ float2 red[kDwCols][32];

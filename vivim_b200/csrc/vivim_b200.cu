@@ -297,7 +297,7 @@ int launch_dw_t(const vv_dwconv3d_args& a, cudaStream_t st) {
 #undef VV_DW_STENCIL
     if (a.dweight) {
         const unsigned gx = (unsigned)((a.channels + 63) / 64);
-        int64_t gy = (4 * sm_count() + gx - 1) / gx;                // ~4 CTAs of 256 threads per SM over the whole grid
+        int64_t gy = (8 * sm_count() + gx - 1) / gx;                // 2 resident CTAs of 256 threads per SM (128 registers), 4 waves
         gy = std::max<int64_t>(1, std::min<int64_t>(gy, (ncols + vv::kDwCols - 1) / vv::kDwCols));
         const dim3 grid(gx, (unsigned)gy), block(32, vv::kDwCols);
         if (pair) vv::dwconv3d_wgrad_kernel<T, true><<<grid, block, 0, st>>>(
